@@ -1,0 +1,669 @@
+// mpc_core.cuh -- per-problem numerics of the batched nonlinear MPC (sm_100a).
+//
+// One problem lives in ONE thread: horizon arrays (controls, nominal states, feedback
+// gains, multipliers, obstacle tracks) sit in a strided shared-memory "slot file"
+// (slot * blockDim + tid -> conflict-free), the 6x6 value-function block sits in
+// registers.  The functions are templated on the scalar type and on nothing
+// CUDA-specific so the test-only host harness (tests/hostsim) can instantiate them
+// with double/float on the CPU; the product library instantiates float on device only.
+//
+// What is computed (reference: SaeedRahmani/MPC-RL_for_AVs, cited as file:line):
+//   dynamics   kinematic bicycle + explicit Euler        agents/pure_mpc.py:220-228,252-254
+//   tracking   4 perp^2 + 2 para^2 + w_v dv^2 + .5 dth^2 agents/pure_mpc.py:128-156
+//   control    0.01 (a^2 + delta^2); input diff          agents/pure_mpc.py:161-165
+//   distance   (1000|100)/(d+1e-6)^2 vs moving obstacles agents/archive/pure_mpc.py:189-206
+//   collision  3000 v^2 when is_collide                  agents/pure_mpc.py:179-183
+//   objective  10 state + w_c control + w_d diff (+...)  agents/pure_mpc.py:204-212
+//   bounds     a, delta, v, theta                        agents/pure_mpc.py:272-280
+// The NLP that the reference hands to CasADi/IPOPT (pure_mpc.py:285-300) is solved here
+// in single-shooting form by a control-limited second-order DDP (exact dynamics Hessian,
+// per-stage 2x2 box QP, saddle-free eigenvalue modification).  The v / theta node bounds
+// have relative degree one under Euler, so they are enforced exactly as state-dependent
+// control boxes (see control_box).  The previous control is carried as two extra state
+// coordinates so the input-difference cost stays stage-wise (state z = x,y,th,v,a-,d-).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define MPC_HD __host__ __device__ __forceinline__
+#else
+#define MPC_HD inline
+#endif
+
+namespace mpcb {
+
+constexpr int kNRef = 85;          // agents/base_agent.py:127-152 (40 + 20 + 25 rows)
+constexpr int kRefStride = 5;      // x, y, heading, sin h, cos h
+constexpr int kMaxObstacles = 16;
+
+template <typename T> struct Lim {
+  static MPC_HD T a_max() { return T(5); }                        // pure_mpc.py:279-280
+  static MPC_HD T d_max() { return T(1.0471975511965976); }       // pi/3
+  static MPC_HD T v_min() { return T(0); }                        // pure_mpc.py:273-274
+  static MPC_HD T v_max() { return T(30); }
+  static MPC_HD T th_max() { return T(3.14159265358979323846); }  // +-pi
+};
+
+// ---- scalar math dispatch ---------------------------------------------------------
+MPC_HD void sincos_(float x, float* s, float* c) {
+#if defined(__CUDA_ARCH__)
+  sincosf(x, s, c);
+#else
+  *s = sinf(x); *c = cosf(x);
+#endif
+}
+MPC_HD void sincos_(double x, double* s, double* c) { *s = sin(x); *c = cos(x); }
+MPC_HD float rsqrt_(float x) {
+#if defined(__CUDA_ARCH__)
+  return rsqrtf(x);
+#else
+  return 1.0f / sqrtf(x);
+#endif
+}
+MPC_HD double rsqrt_(double x) { return 1.0 / sqrt(x); }
+MPC_HD float sqrt_(float x) { return sqrtf(x); }
+MPC_HD double sqrt_(double x) { return sqrt(x); }
+MPC_HD float abs_(float x) { return fabsf(x); }
+MPC_HD double abs_(double x) { return fabs(x); }
+template <typename T> MPC_HD T min_(T a, T b) { return a < b ? a : b; }
+template <typename T> MPC_HD T max_(T a, T b) { return a > b ? a : b; }
+template <typename T> MPC_HD T clamp_(T x, T lo, T hi) { return min_(max_(x, lo), hi); }
+
+// ---- configuration shared by the whole batch ----------------------------------------
+struct SolverConfig {
+  int N;                  // horizon (cfg.yaml:90 ships 16; benchmark 20)
+  int M;                  // obstacle slots per problem
+  float dt;               // 1 / policy_frequency  (base_agent.py:43)
+  float w_distance;       // cfg.yaml:105 (10) in the archive objective; 0 = live agent
+  float w_collision;      // cfg.yaml:106; 0 = live agent
+  int literal_no_collision;  // 1: objective of pure_mpc_no_collision.py:146-151
+  int max_iter;           // DDP iterations per problem (reference: ipopt.max_iter 1000, pure_mpc.py:294)
+  float tol_step;         // convergence: max |du| of the accepted full step
+  float reg_min;          // floor on |eigenvalue| of the regularised Quu
+};
+
+// ---- per-problem scalars -------------------------------------------------------------
+template <typename T> struct ProblemScalars {
+  int ego_index;          // nearest reference row (pure_mpc.py:106-109)
+  int n_obs;              // present obstacles (<= M)
+  int is_collide;
+  T w_speed;              // already 100 when is_collide (pure_mpc.py:143-147)
+  T w_control, w_diff;    // weights_from_RL or cfg defaults (pure_mpc.py:96-104)
+  // reference-speed profile seen by stage k: k < vr_n ? vr_a + k*vr_slope : vr_b
+  // (constant profile: vr_n = 0; regenerated ramp pure_mpc.py:707-716: vr_a = v_ego,
+  //  slope = -v_ego/(n-1), vr_n = n, vr_b = 0)
+  T vr_a, vr_slope, vr_b;
+  int vr_n;
+};
+
+template <typename T> MPC_HD T ref_speed_at(const ProblemScalars<T>& p, int k) {
+  return (k < p.vr_n) ? p.vr_a + T(k) * p.vr_slope : p.vr_b;
+}
+
+// ---- strided slot file ----------------------------------------------------------------
+// base already points at this thread's lane; consecutive slots are `stride` apart.
+template <typename T> struct Slots {
+  T* base;
+  int stride;
+  int N, M;
+  MPC_HD T& at(int s) const { return base[(long)s * stride]; }
+  // layout
+  MPC_HD int oU() const { return 0; }                       // 2N
+  MPC_HD int oX() const { return 2 * N; }                   // 4(N+1)
+  MPC_HD int oK() const { return 2 * N + 4 * (N + 1); }     // 12N
+  MPC_HD int oF() const { return oK() + 12 * N; }           // 2N feed-forward
+  MPC_HD int oO() const { return oF() + 2 * N; }            // 4M obstacles x,y,incx,incy
+  MPC_HD int total() const { return oO() + 4 * M; }
+  MPC_HD T& U(int k, int i) const { return at(oU() + 2 * k + i); }
+  MPC_HD T& X(int k, int i) const { return at(oX() + 4 * k + i); }
+  MPC_HD T& K(int k, int i) const { return at(oK() + 12 * k + i); }   // row-major 2x6
+  MPC_HD T& F(int k, int i) const { return at(oF() + 2 * k + i); }
+  MPC_HD T& O(int m, int i) const { return at(oO() + 4 * m + i); }
+};
+MPC_HD int slots_per_problem(int N, int M) { return 2 * N + 4 * (N + 1) + 12 * N + 2 * N + 4 * M; }
+
+// ---- steering terms -------------------------------------------------------------------
+// beta = atan(0.5 tan delta) (pure_mpc.py:221) expressed without atan/tan:
+// q = cos^2 d + 0.25 sin^2 d, cos b = cos d / sqrt q, sin b = 0.5 sin d / sqrt q,
+// beta' = 0.5 / q, beta'' = 0.75 sin d cos d / q^2.
+template <typename T> struct Steer { T sb, cb, g, h; };
+template <typename T> MPC_HD Steer<T> steer_terms(T delta, bool second) {
+  T sd, cd;
+  sincos_(delta, &sd, &cd);
+  T q = T(1) - T(0.75) * sd * sd;
+  T r = rsqrt_(q);
+  Steer<T> o;
+  o.cb = cd * r;
+  o.sb = T(0.5) * sd * r;
+  T iq = T(1) / q;
+  o.g = T(0.5) * iq;
+  o.h = second ? T(0.75) * sd * cd * iq * iq : T(0);
+  return o;
+}
+
+// one Euler step (pure_mpc.py:252-254) given sin/cos of theta and the steering terms
+template <typename T>
+MPC_HD void euler_step(T& x, T& y, T& th, T& v, T a, const Steer<T>& st, T dt, T* c_out = nullptr, T* s_out = nullptr) {
+  T sth, cth;
+  sincos_(th, &sth, &cth);
+  T c = cth * st.cb - sth * st.sb;     // cos(theta + beta)
+  T s = sth * st.cb + cth * st.sb;     // sin(theta + beta)
+  if (c_out) { *c_out = c; *s_out = s; }
+  x += dt * v * c;
+  y += dt * v * s;
+  th += dt * v * st.sb * T(1.0 / 2.5);  // agents/utils.py:18 wheelbase 2.5
+  v += dt * a;
+}
+
+// ---- stage cost (value only) ------------------------------------------------------------
+// comp[0..5] accumulate the reference's six un-weighted components (pure_mpc.py:215-216);
+// returns the weighted stage objective (pure_mpc.py:204-212 + archive terms).
+template <typename T>
+MPC_HD T stage_cost(const SolverConfig& cfg, const ProblemScalars<T>& p, const T* __restrict__ ref,
+                    const Slots<T>& sl, int k, T x, T y, T th, T v, T a, T d, T ap, T dp, T* comp) {
+  int j = p.ego_index + k;
+  j = j < kNRef - 1 ? j : kNRef - 1;
+  const T* r = ref + j * kRefStride;
+  T dx = x - r[0], dy = y - r[1];
+  T perp = dx * r[3] - dy * r[4];
+  T para = dx * r[4] + dy * r[3];
+  T dv = v - ref_speed_at(p, k);
+  T dth = th - r[2];
+  T st = T(4) * perp * perp + T(2) * para * para + p.w_speed * dv * dv + T(0.5) * dth * dth;
+  T ct = T(0.01) * (a * a + d * d);
+  T df = T(0);
+  if (k > 0) { T ea = a - ap, ed = d - dp; df = T(0.01) * (ea * ea + ed * ed); }
+  T dist = T(0);
+  if (cfg.w_distance != 0.f || comp) {
+    for (int m = 0; m < p.n_obs; ++m) {
+      T ex = x - (sl.O(m, 0) + T(k) * sl.O(m, 2));
+      T ey = y - (sl.O(m, 1) + T(k) * sl.O(m, 3));
+      T d2 = ex * ex + ey * ey;
+      T dd = sqrt_(d2);
+      T e = dd + T(1e-6);
+      T c = dd < T(1) ? T(1000) : T(100);
+      dist += c / (e * e);
+    }
+  }
+  T col = p.is_collide ? T(3000) * v * v : T(0);
+  if (comp) { comp[0] += st; comp[1] += ct; comp[3] += df; comp[4] += dist; comp[5] += col; }
+  if (cfg.literal_no_collision) return p.w_control * ct + p.w_diff * df;
+  return T(10) * st + p.w_control * ct + p.w_diff * df + T(cfg.w_distance) * dist + T(cfg.w_collision) * col;
+}
+
+// ---- state bounds as state-dependent control boxes ------------------------------------------
+// The reference bounds every shooting node: 0 <= v_k <= 30, |theta_k| <= pi (pure_mpc.py:272-274).
+// With Euler dynamics both have relative degree one: v_{k+1} = v_k + dt a_k and
+// theta_{k+1} = theta_k + dt (v_k / L) sin beta(delta_k), so "node k+1 inside its bounds" is the
+// same set as a box on u_k whose edges depend on (theta_k, v_k).  The forward pass clamps to
+// that box exactly (every iterate is feasible); the backward pass treats a control sitting on a
+// state-dependent edge as the affine policy du = d(edge)/dx dx, i.e. the active-set SQP step.
+template <typename T> struct Box {
+  T lo_a, hi_a, lo_d, hi_d;
+  bool sa_lo, sa_hi, sd_lo, sd_hi;   // edge comes from a state bound (not the constant limit)
+};
+template <typename T> MPC_HD T sb_max() { return T(0.6546536707079771); }   // sin beta(pi/3)
+MPC_HD float asin_(float x) { return asinf(x); }
+MPC_HD double asin_(double x) { return asin(x); }
+// inverse of sin beta(delta) = 0.5 sin d / sqrt(1 - 0.75 sin^2 d)
+template <typename T> MPC_HD T delta_of_sinbeta(T sb) {
+  sb = clamp_(sb, -sb_max<T>(), sb_max<T>());
+  return asin_(sb * rsqrt_(T(0.25) + T(0.75) * sb * sb));
+}
+template <typename T> MPC_HD Box<T> control_box(T th, T v, T dt) {
+  Box<T> b;
+  b.lo_a = -Lim<T>::a_max(); b.hi_a = Lim<T>::a_max();
+  b.lo_d = -Lim<T>::d_max(); b.hi_d = Lim<T>::d_max();
+  b.sa_lo = b.sa_hi = b.sd_lo = b.sd_hi = false;
+  const T idt = T(1) / dt;
+  T ha = (Lim<T>::v_max() - v) * idt, la = (Lim<T>::v_min() - v) * idt;
+  if (ha < b.hi_a) { b.hi_a = ha; b.sa_hi = true; }
+  if (la > b.lo_a) { b.lo_a = la; b.sa_lo = true; }
+  if (b.hi_a < b.lo_a) { b.hi_a = b.lo_a; }                 // v0 outside [0, 30]: keep a defined box
+  const T gain = dt * v * T(1.0 / 2.5);                      // d theta+ / d sin beta
+  const T reach = gain * sb_max<T>();
+  if (th + reach > Lim<T>::th_max()) { b.hi_d = delta_of_sinbeta((Lim<T>::th_max() - th) / gain); b.sd_hi = true; }
+  if (th - reach < -Lim<T>::th_max()) { b.lo_d = delta_of_sinbeta((-Lim<T>::th_max() - th) / gain); b.sd_lo = true; }
+  if (b.hi_d < b.lo_d) { b.hi_d = b.lo_d; }
+  return b;
+}
+
+// ---- open-loop rollout of the stored controls; fills X, returns the objective ----------------
+// Controls are used as stored (no clamping): this is also the parity entry point for
+// "rollout + six cost components" (mpc_rollout_cost).
+template <typename T>
+MPC_HD T rollout_nominal(const SolverConfig& cfg, const ProblemScalars<T>& p, const T* __restrict__ ref,
+                         const Slots<T>& sl, T* comp /*6 or null*/) {
+  const int N = cfg.N;
+  T x = sl.X(0, 0), y = sl.X(0, 1), th = sl.X(0, 2), v = sl.X(0, 3);
+  T J = T(0), ap = T(0), dp = T(0);
+  for (int k = 0; k < N; ++k) {
+    T a = sl.U(k, 0), d = sl.U(k, 1);
+    J += stage_cost(cfg, p, ref, sl, k, x, y, th, v, a, d, ap, dp, comp);
+    Steer<T> st = steer_terms(d, false);
+    euler_step(x, y, th, v, a, st, T(cfg.dt));
+    sl.X(k + 1, 0) = x; sl.X(k + 1, 1) = y; sl.X(k + 1, 2) = th; sl.X(k + 1, 3) = v;
+    ap = a; dp = d;
+  }
+  return J;
+}
+
+// ---- 2x2 box QP --------------------------------------------------------------------------
+// min 1/2 d'Hd + g'd, lo <= d <= hi, H positive definite.  Exact: the Newton point if it is
+// inside, otherwise the best of the four edge minimisers.  side[i] = 0 free, -1 at lo, +1 at hi.
+template <typename T>
+MPC_HD void box_qp2(T h00, T h01, T h11, T g0, T g1, T lo0, T hi0, T lo1, T hi1, T* d0, T* d1, int* side0, int* side1) {
+  T idet = T(1) / (h00 * h11 - h01 * h01);
+  T n0 = -(h11 * g0 - h01 * g1) * idet;
+  T n1 = -(h00 * g1 - h01 * g0) * idet;
+  if (n0 >= lo0 && n0 <= hi0 && n1 >= lo1 && n1 <= hi1) { *d0 = n0; *d1 = n1; *side0 = 0; *side1 = 0; return; }
+  T best = T(1e30), b0 = T(0), b1 = T(0);
+  int s0 = 0, s1 = 0;
+  const T ih11 = T(1) / h11, ih00 = T(1) / h00;
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {          // coordinate 0 pinned to an edge
+    T f0 = e ? hi0 : lo0;
+    T u1 = -(g1 + h01 * f0) * ih11;
+    int t1 = u1 <= lo1 ? -1 : (u1 >= hi1 ? 1 : 0);
+    u1 = clamp_(u1, lo1, hi1);
+    T val = T(0.5) * (h00 * f0 * f0 + T(2) * h01 * f0 * u1 + h11 * u1 * u1) + g0 * f0 + g1 * u1;
+    if (val < best) { best = val; b0 = f0; b1 = u1; s0 = e ? 1 : -1; s1 = t1; }
+  }
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {          // coordinate 1 pinned to an edge
+    T f1 = e ? hi1 : lo1;
+    T u0 = -(g0 + h01 * f1) * ih00;
+    int t0 = u0 <= lo0 ? -1 : (u0 >= hi0 ? 1 : 0);
+    u0 = clamp_(u0, lo0, hi0);
+    T val = T(0.5) * (h00 * u0 * u0 + T(2) * h01 * u0 * f1 + h11 * f1 * f1) + g0 * u0 + g1 * f1;
+    if (val < best) { best = val; b0 = u0; b1 = f1; s0 = t0; s1 = e ? 1 : -1; }
+  }
+  *d0 = b0; *d1 = b1; *side0 = s0; *side1 = s1;
+}
+
+// symmetric 6x6 in 21 registers, upper triangle, row-major
+MPC_HD constexpr int sym6(int i, int j) { return i <= j ? (i * (13 - i)) / 2 + (j - i) : (j * (13 - j)) / 2 + (i - j); }
+
+// ---- backward pass -------------------------------------------------------------------------
+// Fills K (2x6 per stage) and F (feed-forward) from the nominal (X, U); returns the two
+// coefficients of the predicted objective change  dJ(alpha) = alpha*d1 + alpha^2*d2.
+template <typename T>
+MPC_HD void backward_pass(const SolverConfig& cfg, const ProblemScalars<T>& p, const T* __restrict__ ref,
+                          const Slots<T>& sl, T mu, T hs, T* d1_out, T* d2_out) {
+  // hs in [0,1] scales the second-order dynamics terms and the negative (tangential) obstacle
+  // curvature: 0 = Gauss-Newton/iLQR model (robust far from the solution), 1 = exact Hessian.
+  const int N = cfg.N;
+  const T dt = T(cfg.dt);
+  const T iL = T(1.0 / 2.5);
+  T P[21], pv[6];                 // value function of stage k+1 (x_N carries no cost: pure_mpc.py:128,204-212)
+#pragma unroll
+  for (int i = 0; i < 21; ++i) P[i] = T(0);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) pv[i] = T(0);
+  T d1 = T(0), d2 = T(0);
+  const T cc2 = T(0.02) * p.w_control;
+  for (int k = N - 1; k >= 0; --k) {
+    const T x = sl.X(k, 0), y = sl.X(k, 1), th = sl.X(k, 2), v = sl.X(k, 3);
+    const T a = sl.U(k, 0), d = sl.U(k, 1);
+    const T cd2 = k > 0 ? T(0.02) * p.w_diff : T(0);
+    T ap = T(0), dp = T(0);
+    if (k > 0) { ap = sl.U(k - 1, 0); dp = sl.U(k - 1, 1); }
+    // ---- dynamics derivatives
+    Steer<T> st = steer_terms(d, true);
+    T sth, cth;
+    sincos_(th, &sth, &cth);
+    const T c = cth * st.cb - sth * st.sb, s = sth * st.cb + cth * st.sb;
+    const T a13 = -dt * v * s, a14 = dt * c, a23 = dt * v * c, a24 = dt * s, a34 = dt * st.sb * iL;
+    const T b1 = a13 * st.g, b2 = a23 * st.g, b3 = dt * v * iL * st.cb * st.g;
+    // ---- stage cost derivatives wrt state
+    T lx = T(0), ly = T(0), lth = T(0), lv = T(0);
+    T lxx = T(0), lxy = T(0), lyy = T(0), lthth = T(0), lvv = T(0);
+    if (!cfg.literal_no_collision) {
+      int j = p.ego_index + k;
+      j = j < kNRef - 1 ? j : kNRef - 1;
+      const T* r = ref + j * kRefStride;
+      const T sh = r[3], ch = r[4];
+      T dx = x - r[0], dy = y - r[1];
+      T perp = dx * sh - dy * ch, para = dx * ch + dy * sh;
+      lx = T(80) * perp * sh + T(40) * para * ch;
+      ly = -T(80) * perp * ch + T(40) * para * sh;
+      lth = T(10) * (th - r[2]);
+      T wv = T(20) * p.w_speed;
+      lv = wv * (v - ref_speed_at(p, k));
+      lxx = T(80) * sh * sh + T(40) * ch * ch;
+      lxy = -T(40) * sh * ch;
+      lyy = T(80) * ch * ch + T(40) * sh * sh;
+      lthth = T(10);
+      lvv = wv;
+      if (cfg.w_distance != 0.f) {
+        const T wd = T(cfg.w_distance);
+        for (int m = 0; m < p.n_obs; ++m) {
+          T ex = x - (sl.O(m, 0) + T(k) * sl.O(m, 2));
+          T ey = y - (sl.O(m, 1) + T(k) * sl.O(m, 3));
+          T d2_ = ex * ex + ey * ey;
+          T dd = sqrt_(d2_);
+          T e = dd + T(1e-6);
+          T cw = wd * (dd < T(1) ? T(1000) : T(100));
+          T ie = T(1) / e;
+          T ie2 = ie * ie;
+          T idd = T(1) / max_(dd, T(1e-12));
+          T f1 = -T(2) * cw * ie2 * ie;          // phi'(d)
+          T f2 = T(6) * cw * ie2 * ie2;          // phi''(d)
+          T nx = ex * idd, ny = ey * idd;
+          T tang = hs * f1 * idd;                 // phi'/d  (negative: tangential curvature)
+          lx += f1 * nx; ly += f1 * ny;
+          T rad = f2 - tang;
+          lxx += rad * nx * nx + tang;
+          lxy += rad * nx * ny;
+          lyy += rad * ny * ny + tang;
+        }
+      }
+      if (cfg.w_collision != 0.f && p.is_collide) {
+        lv += T(6000) * T(cfg.w_collision) * v;
+        lvv += T(6000) * T(cfg.w_collision);
+      }
+    }
+    // ---- contractions with the next-stage costate (second-order DDP terms)
+    const T p1 = pv[0], p2 = pv[1], p3 = pv[2], p4 = pv[3];
+    const T mm = p1 * c + p2 * s, nn = -p1 * s + p2 * c;
+    const T Hthth = hs * (-dt * v * mm);
+    const T Hthv = hs * (dt * nn);
+    const T Hthd = hs * (-dt * v * st.g * mm);
+    const T Hvd = hs * (dt * st.g * nn + p3 * dt * iL * st.cb * st.g);
+    const T Hdd = hs * (dt * v * (-st.g * st.g * mm + st.h * nn) + p3 * dt * v * iL * (-st.sb * st.g * st.g + st.cb * st.h));
+    // ---- Qz, Qu
+    T Qz[6], Qu[2];
+    Qz[0] = lx + p1;
+    Qz[1] = ly + p2;
+    Qz[2] = lth + p3 + dt * v * nn;
+    Qz[3] = lv + p4 + dt * mm + p3 * a34;
+    Qz[4] = -cd2 * (a - ap);
+    Qz[5] = -cd2 * (d - dp);
+    Qu[0] = cc2 * a + cd2 * (a - ap) + dt * p4 + pv[4];
+    Qu[1] = cc2 * d + cd2 * (d - dp) + b1 * p1 + b2 * p2 + b3 * p3 + pv[5];
+    // ---- M = Pss A (4x4), W = Pus A (2x4)
+    T Mx[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      T pi0 = P[sym6(i, 0)], pi1 = P[sym6(i, 1)], pi2 = P[sym6(i, 2)], pi3 = P[sym6(i, 3)];
+      Mx[i][0] = pi0;
+      Mx[i][1] = pi1;
+      Mx[i][2] = pi2 + a13 * pi0 + a23 * pi1;
+      Mx[i][3] = pi3 + a14 * pi0 + a24 * pi1 + a34 * pi2;
+    }
+    T W[2][4];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      T q0 = P[sym6(4 + r, 0)], q1 = P[sym6(4 + r, 1)], q2 = P[sym6(4 + r, 2)], q3 = P[sym6(4 + r, 3)];
+      W[r][0] = q0;
+      W[r][1] = q1;
+      W[r][2] = q2 + a13 * q0 + a23 * q1;
+      W[r][3] = q3 + a14 * q0 + a24 * q1 + a34 * q2;
+    }
+    // ---- Quz (2x6)
+    T Quz[2][6];
+#pragma unroll
+    for (int jc = 0; jc < 4; ++jc) {
+      Quz[0][jc] = dt * Mx[3][jc] + W[0][jc];
+      Quz[1][jc] = b1 * Mx[0][jc] + b2 * Mx[1][jc] + b3 * Mx[2][jc] + W[1][jc];
+    }
+    Quz[1][2] += Hthd;
+    Quz[1][3] += Hvd;
+    Quz[0][4] = -cd2; Quz[0][5] = T(0);
+    Quz[1][4] = T(0); Quz[1][5] = -cd2;
+    // ---- Quu
+    T PBd[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) PBd[i] = b1 * P[sym6(i, 0)] + b2 * P[sym6(i, 1)] + b3 * P[sym6(i, 2)];
+    T BPa0 = dt * P[sym6(3, 4)], BPa1 = dt * P[sym6(3, 5)];
+    T BPd0 = b1 * P[sym6(0, 4)] + b2 * P[sym6(1, 4)] + b3 * P[sym6(2, 4)];
+    T BPd1 = b1 * P[sym6(0, 5)] + b2 * P[sym6(1, 5)] + b3 * P[sym6(2, 5)];
+    const T luu = cc2 + cd2;
+    T Quu00 = luu + dt * dt * P[sym6(3, 3)] + T(2) * BPa0 + P[sym6(4, 4)];
+    T Quu01 = dt * PBd[3] + BPa1 + BPd0 + P[sym6(4, 5)];
+    T Quu11 = luu + b1 * PBd[0] + b2 * PBd[1] + b3 * PBd[2] + T(2) * BPd1 + P[sym6(5, 5)] + Hdd;
+    // ---- Qzz (sym 6x6): state block A'M + lss + H, (up,up) = cd2 I
+    T Qzz[21];
+#pragma unroll
+    for (int i = 0; i < 21; ++i) Qzz[i] = T(0);
+    Qzz[sym6(0, 0)] = Mx[0][0] + lxx;
+    Qzz[sym6(0, 1)] = Mx[0][1] + lxy;
+    Qzz[sym6(0, 2)] = Mx[0][2];
+    Qzz[sym6(0, 3)] = Mx[0][3];
+    Qzz[sym6(1, 1)] = Mx[1][1] + lyy;
+    Qzz[sym6(1, 2)] = Mx[1][2];
+    Qzz[sym6(1, 3)] = Mx[1][3];
+    Qzz[sym6(2, 2)] = Mx[2][2] + a13 * Mx[0][2] + a23 * Mx[1][2] + lthth + Hthth;
+    Qzz[sym6(2, 3)] = Mx[2][3] + a13 * Mx[0][3] + a23 * Mx[1][3] + Hthv;
+    Qzz[sym6(3, 3)] = Mx[3][3] + a14 * Mx[0][3] + a24 * Mx[1][3] + a34 * Mx[2][3] + lvv;
+    Qzz[sym6(4, 4)] = cd2;
+    Qzz[sym6(5, 5)] = cd2;
+    // ---- regularise Quu: replace its eigenvalues l by max(|l|, reg_min) + mu (saddle-free
+    // modification; a uniform shift would cripple the healthy direction whenever the
+    // second-order dynamics terms make the other one strongly negative)
+    T h00 = Quu00, h01 = Quu01, h11 = Quu11;
+    {
+      T hm = T(0.5) * (h00 + h11), hd = T(0.5) * (h00 - h11);
+      T rr = sqrt_(hd * hd + h01 * h01);
+      T l1 = hm - rr, l2 = hm + rr;
+      T n1 = max_(abs_(l1), T(cfg.reg_min)), n2 = max_(abs_(l2), T(cfg.reg_min));
+      if (rr > T(1e-12) * (abs_(hm) + T(1e-30))) {
+        T i2r = T(0.5) / rr;
+        T c0 = (n1 * l2 - n2 * l1) * i2r, c1 = (n2 - n1) * i2r;
+        h00 = c0 + c1 * h00; h01 = c1 * h01; h11 = c0 + c1 * h11;
+      } else {
+        h00 = n1; h01 = T(0); h11 = n1;
+      }
+    }
+    // ---- Levenberg term on the *next state* (mu |dz'|^2): keeps the new trajectory near the
+    // nominal where the expansion holds; dz' = A dz + B du, plus the carried control
+    const T f00 = h00, f01 = h01, f11 = h11;   // modified Quu without the Levenberg term
+    T Rz[2][6];
+#pragma unroll
+    for (int jc = 0; jc < 6; ++jc) { Rz[0][jc] = Quz[0][jc]; Rz[1][jc] = Quz[1][jc]; }
+    if (mu > T(0)) {
+      h00 += mu * (dt * dt + T(1));
+      h11 += mu * (b1 * b1 + b2 * b2 + b3 * b3 + T(1));
+      Rz[0][3] += mu * dt;
+      Rz[1][0] += mu * b1;
+      Rz[1][1] += mu * b2;
+      Rz[1][2] += mu * (b1 * a13 + b2 * a23 + b3);
+      Rz[1][3] += mu * (b1 * a14 + b2 * a24 + b3 * a34);
+    }
+    // ---- box QP for the feed-forward on the (state-dependent) control box of this node
+    const Box<T> bx = control_box(th, v, dt);
+    T k0, k1;
+    int s0, s1;
+    box_qp2(h00, h01, h11, Qu[0], Qu[1], bx.lo_a - a, bx.hi_a - a, bx.lo_d - d, bx.hi_d - d, &k0, &k1, &s0, &s1);
+    // ---- gains: pinned coordinates follow their edge (constant edge: zero gain; edge that
+    // comes from a node bound: d(edge)/dx), free coordinates minimise the model given those.
+    // E = the control Hessian of the model that is actually minimised: the modified matrix on
+    // the free block, the true curvature along pinned coordinates.  The same E is used in the
+    // value recursion, otherwise negative curvature compounds backwards through the horizon.
+    T Kg[2][6];
+#pragma unroll
+    for (int jc = 0; jc < 6; ++jc) { Kg[0][jc] = T(0); Kg[1][jc] = T(0); }
+    if (s0 != 0 && ((s0 > 0) ? bx.sa_hi : bx.sa_lo)) Kg[0][3] = -T(1) / dt;          // keeps v+ on its bound
+    if (s1 != 0 && ((s1 > 0) ? bx.sd_hi : bx.sd_lo) && b3 > T(1e-12)) {              // keeps theta+ on its bound
+      T ib3 = T(1) / b3;
+      Kg[1][2] = -ib3;
+      Kg[1][3] = -a34 * ib3;
+    }
+    // pinned coordinates: true curvature along the edge policy, negative part dropped (the
+    // edge's own curvature is not modelled, so a negative value is not trustworthy)
+    T E00 = max_(Quu00, T(0)), E01 = Quu01, E11 = max_(Quu11, T(0));
+    if (s0 == 0 && s1 == 0) {
+      E00 = f00; E01 = f01; E11 = f11;
+      T idet = T(1) / (h00 * h11 - h01 * h01);
+#pragma unroll
+      for (int jc = 0; jc < 6; ++jc) {
+        Kg[0][jc] = -(h11 * Rz[0][jc] - h01 * Rz[1][jc]) * idet;
+        Kg[1][jc] = -(h00 * Rz[1][jc] - h01 * Rz[0][jc]) * idet;
+      }
+    } else if (s0 == 0) {
+      E00 = max_(abs_(Quu00), T(cfg.reg_min)) + mu * (dt * dt + T(1));
+      T ih = T(1) / E00;
+      k0 = clamp_(-(Qu[0] + E01 * k1) * ih, bx.lo_a - a, bx.hi_a - a);
+#pragma unroll
+      for (int jc = 0; jc < 6; ++jc) Kg[0][jc] = -(Rz[0][jc] + E01 * Kg[1][jc]) * ih;
+    } else if (s1 == 0) {
+      E11 = max_(abs_(Quu11), T(cfg.reg_min)) + mu * (b1 * b1 + b2 * b2 + b3 * b3 + T(1));
+      T ih = T(1) / E11;
+      k1 = clamp_(-(Qu[1] + E01 * k0) * ih, bx.lo_d - d, bx.hi_d - d);
+#pragma unroll
+      for (int jc = 0; jc < 6; ++jc) Kg[1][jc] = -(Rz[1][jc] + E01 * Kg[0][jc]) * ih;
+    }
+#if defined(MPC_TRACE2) && !defined(__CUDA_ARCH__)
+    printf("  k %d Quu %.4g %.4g %.4g Hdd %.4g Qu %.4g %.4g kff %.4g %.4g side %d %d box d [%.4g %.4g] sd %d %d P22 %.4g P33 %.4g p %.3g %.3g %.3g %.3g\n", k, (double)Quu00, (double)Quu01, (double)Quu11, (double)Hdd,
+           (double)Qu[0], (double)Qu[1], (double)k0, (double)k1, s0, s1, (double)bx.lo_d, (double)bx.hi_d, (int)bx.sd_lo, (int)bx.sd_hi, (double)P[sym6(2,2)], (double)P[sym6(3,3)], (double)pv[0], (double)pv[1], (double)pv[2], (double)pv[3]);
+#endif
+    sl.F(k, 0) = k0; sl.F(k, 1) = k1;
+#pragma unroll
+    for (int jc = 0; jc < 6; ++jc) { sl.K(k, jc) = Kg[0][jc]; sl.K(k, 6 + jc) = Kg[1][jc]; }
+    // ---- predicted change and value update
+    T Qk0 = E00 * k0 + E01 * k1, Qk1 = E01 * k0 + E11 * k1;
+    d1 += k0 * Qu[0] + k1 * Qu[1];
+    d2 += T(0.5) * (k0 * Qk0 + k1 * Qk1);
+    T t0 = Qk0 + Qu[0], t1 = Qk1 + Qu[1];
+    T Tm[2][6];
+#pragma unroll
+    for (int jc = 0; jc < 6; ++jc) {
+      Tm[0][jc] = E00 * Kg[0][jc] + E01 * Kg[1][jc] + Quz[0][jc];
+      Tm[1][jc] = E01 * Kg[0][jc] + E11 * Kg[1][jc] + Quz[1][jc];
+      pv[jc] = Qz[jc] + Kg[0][jc] * t0 + Kg[1][jc] * t1 + Quz[0][jc] * k0 + Quz[1][jc] * k1;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int jc = i; jc < 6; ++jc)
+        P[sym6(i, jc)] = Qzz[sym6(i, jc)] + Kg[0][i] * Tm[0][jc] + Kg[1][i] * Tm[1][jc] +
+                         Quz[0][i] * Kg[0][jc] + Quz[1][i] * Kg[1][jc];
+  }
+  *d1_out = d1;
+  *d2_out = d2;
+}
+
+// ---- closed-loop forward pass -----------------------------------------------------------------
+// kCommit=false: evaluate the objective of step length alpha without touching the nominal.
+// kCommit=true : overwrite (X, U) in place with the new trajectory.  Returns the objective;
+// *maxdu = max |u_new - u_old| over the horizon.
+template <typename T, bool kCommit>
+MPC_HD T forward_pass(const SolverConfig& cfg, const ProblemScalars<T>& p, const T* __restrict__ ref,
+                      const Slots<T>& sl, T alpha, T* maxdu) {
+  const int N = cfg.N;
+  const T dt = T(cfg.dt);
+  T x = sl.X(0, 0), y = sl.X(0, 1), th = sl.X(0, 2), v = sl.X(0, 3);
+  T J = T(0), ap = T(0), dp = T(0), dap = T(0), ddp = T(0), md = T(0);
+  for (int k = 0; k < N; ++k) {
+    T ex = x - sl.X(k, 0), ey = y - sl.X(k, 1), eth = th - sl.X(k, 2), ev = v - sl.X(k, 3);
+    T ua = sl.U(k, 0), ud = sl.U(k, 1);
+    T da = alpha * sl.F(k, 0) + sl.K(k, 0) * ex + sl.K(k, 1) * ey + sl.K(k, 2) * eth + sl.K(k, 3) * ev +
+           sl.K(k, 4) * dap + sl.K(k, 5) * ddp;
+    T dd = alpha * sl.F(k, 1) + sl.K(k, 6) * ex + sl.K(k, 7) * ey + sl.K(k, 8) * eth + sl.K(k, 9) * ev +
+           sl.K(k, 10) * dap + sl.K(k, 11) * ddp;
+    const Box<T> bx = control_box(th, v, dt);
+    T a = clamp_(ua + da, bx.lo_a, bx.hi_a);
+    T d = clamp_(ud + dd, bx.lo_d, bx.hi_d);
+    dap = a - ua; ddp = d - ud;
+    md = max_(md, max_(abs_(dap), abs_(ddp)));
+    J += stage_cost(cfg, p, ref, sl, k, x, y, th, v, a, d, ap, dp, (T*)nullptr);
+    if (kCommit) {
+      sl.X(k, 0) = x; sl.X(k, 1) = y; sl.X(k, 2) = th; sl.X(k, 3) = v;
+      sl.U(k, 0) = a; sl.U(k, 1) = d;
+    }
+    Steer<T> st = steer_terms(d, false);
+    euler_step(x, y, th, v, a, st, dt);
+    ap = a; dp = d;
+  }
+  if (kCommit) { sl.X(N, 0) = x; sl.X(N, 1) = y; sl.X(N, 2) = th; sl.X(N, 3) = v; }
+  *maxdu = md;
+  return J;
+}
+
+// status bits returned per problem
+enum : int {
+  kStatusConverged = 0,
+  kStatusMaxIter = 1,        // iteration cap hit (the iterate is still returned, like the reference's print-only failure path pure_mpc.py:303-305)
+  kStatusLineSearchFail = 2, // no acceptable step at maximum regularisation
+  kStatusNaN = 4,
+  kStatusInfeasibleStart = 8 // s0 violates a state bound (the reference NLP is infeasible)
+};
+
+// ---- per-thread solver state -------------------------------------------------------------------
+template <typename T> struct SolveState {
+  T J, mu, hs;
+  int iter, status;
+  bool done;
+};
+
+template <typename T>
+MPC_HD void solve_begin(const SolverConfig& cfg, const ProblemScalars<T>& p, const T* __restrict__ ref,
+                        const Slots<T>& sl, SolveState<T>& s) {
+  for (int k = 0; k < cfg.N; ++k) { sl.U(k, 0) = T(0); sl.U(k, 1) = T(0); }   // cold start (pure_mpc.py:244)
+  s.mu = T(0); s.hs = T(1);
+  s.iter = 0; s.status = 0; s.done = false;
+  T v0 = sl.X(0, 3), th0 = sl.X(0, 2);
+  if (v0 < Lim<T>::v_min() || v0 > Lim<T>::v_max() || abs_(th0) > Lim<T>::th_max() * T(1.000001)) s.status |= kStatusInfeasibleStart;
+  s.J = rollout_nominal(cfg, p, ref, sl, (T*)nullptr);
+}
+
+template <typename T> struct Eps;
+template <> struct Eps<float> { static MPC_HD float v() { return 1.1920929e-7f; } };
+template <> struct Eps<double> { static MPC_HD double v() { return 2.220446049250313e-16; } };
+
+
+// Armijo test with a floor at the rounding noise of the objective: once the predicted decrease
+// is below what the scalar type can resolve, a step that does not make the objective
+// measurably worse is accepted (termination is then decided on the step size).
+template <typename T> MPC_HD bool accept_step(T J, T Jn, T expected) {
+  T noise = T(32) * Eps<T>::v() * (abs_(J) + T(1));
+  if (!(Jn == Jn)) return false;
+  if (Jn <= J + T(1e-4) * expected) return true;
+  return (expected > -noise) && (Jn <= J + noise);
+}
+
+constexpr int kMaxLineSearch = 8;      // alpha = 1, 1/2, ..., 1/128
+
+// bookkeeping after a line search; sets s.done when converged or failed.
+template <typename T>
+MPC_HD void after_line_search(const SolverConfig& cfg, SolveState<T>& s, bool accepted, T alpha, T Jn, T maxdu) {
+  s.iter++;
+  if (accepted) {
+    s.J = Jn;
+    s.mu = s.mu > T(1e-3) ? s.mu * T(0.1) : T(0);
+    if (alpha == T(1) && maxdu < T(cfg.tol_step)) s.done = true;
+  } else {
+    s.mu = max_(s.mu * T(10), T(0.1));
+    if (s.mu > T(1e9)) { s.status |= kStatusLineSearchFail; s.done = true; }
+  }
+  if (!s.done && s.iter >= cfg.max_iter) { s.status |= kStatusMaxIter; s.done = true; }
+}
+
+// straight-line single-problem driver (host harness; the kernel runs the same sub-steps with
+// a warp-synchronous line search, see mpc_kernels.cu)
+template <typename T>
+MPC_HD void solve_one(const SolverConfig& cfg, const ProblemScalars<T>& p, const T* __restrict__ ref,
+                      const Slots<T>& sl, SolveState<T>& s) {
+  solve_begin(cfg, p, ref, sl, s);
+  while (!s.done) {
+    T d1, d2;
+    backward_pass(cfg, p, ref, sl, s.mu, s.hs, &d1, &d2);
+    T alpha = T(1), Jn = T(0), md = T(0);
+    bool acc = false;
+    for (int t = 0; t < kMaxLineSearch && !acc; ++t) {
+      Jn = forward_pass<T, false>(cfg, p, ref, sl, alpha, &md);
+      acc = accept_step(s.J, Jn, alpha * d1 + alpha * alpha * d2);
+      if (!acc) alpha *= T(0.5);
+    }
+    if (acc) Jn = forward_pass<T, true>(cfg, p, ref, sl, alpha, &md);
+#if defined(MPC_TRACE) && !defined(__CUDA_ARCH__)
+    printf("it %d J %.9g d1 %.4g d2 %.4g alpha %.4g acc %d Jn %.9g maxdu %.3g mu %.3g hs %g u0 %.6f %.6f\n", s.iter, (double)s.J,
+           (double)d1, (double)d2, (double)alpha, (int)acc, (double)Jn, (double)md, (double)s.mu, (double)s.hs, (double)sl.U(0, 0), (double)sl.U(0, 1));
+#endif
+    after_line_search(cfg, s, acc, alpha, Jn, md);
+  }
+  if (!(s.J == s.J)) s.status |= kStatusNaN;
+}
+
+}  // namespace mpcb

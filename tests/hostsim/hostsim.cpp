@@ -1,0 +1,143 @@
+// TEST-ONLY host harness.  Compiles the kernel's per-problem device functions
+// (mpc-rl_for_avs_b200/csrc/mpc_core.cuh) with g++ so that the solver LOGIC can be exercised
+// against the oracle on machines without a GPU (`pytest -m "not gpu"`), in float (the
+// device arithmetic) and in double (to separate algorithmic from rounding effects).
+// It is NOT part of the product: the package never loads this library and has no CPU path.
+#include <cstring>
+#include <vector>
+
+#include "../../mpc-rl_for_avs_b200/csrc/mpc_core.cuh"
+
+using namespace mpcb;
+
+struct HsBatch {               // same SoA layout as MpcProblemBatch (include/mpc_b200.h), host memory
+  const float* s0;             // [4][B]
+  const int* ego_index;        // [B]
+  const float* w_speed;        // [B]
+  const float* w_control;      // [B]
+  const float* w_diff;         // [B]
+  const float* vr_a;           // [B]
+  const float* vr_slope;       // [B]
+  const float* vr_b;           // [B]
+  const int* vr_n;             // [B]
+  const unsigned char* is_collide;  // [B]
+  const int* n_obs;            // [B]
+  const float* obstacles;      // [M][4][B]
+};
+
+template <typename T>
+static void load_problem(const HsBatch& b, int B, int i, const SolverConfig& cfg, ProblemScalars<T>& p, Slots<T>& sl) {
+  p.ego_index = b.ego_index[i];
+  p.n_obs = b.n_obs ? b.n_obs[i] : 0;
+  if (p.n_obs > cfg.M) p.n_obs = cfg.M;
+  p.is_collide = b.is_collide ? b.is_collide[i] : 0;
+  p.w_speed = T(b.w_speed[i]);
+  p.w_control = T(b.w_control[i]);
+  p.w_diff = T(b.w_diff[i]);
+  p.vr_a = T(b.vr_a[i]); p.vr_slope = T(b.vr_slope[i]); p.vr_b = T(b.vr_b[i]); p.vr_n = b.vr_n[i];
+  for (int c = 0; c < 4; ++c) sl.X(0, c) = T(b.s0[(size_t)c * B + i]);
+  for (int m = 0; m < cfg.M; ++m)
+    for (int c = 0; c < 4; ++c) sl.O(m, c) = b.obstacles ? T(b.obstacles[((size_t)m * 4 + c) * B + i]) : T(0);
+}
+
+template <typename T>
+static void make_ref(const double* ref85x4, std::vector<T>& out) {
+  out.resize(kNRef * kRefStride);
+  for (int j = 0; j < kNRef; ++j) {
+    out[j * 5 + 0] = T(ref85x4[j * 4 + 0]);
+    out[j * 5 + 1] = T(ref85x4[j * 4 + 1]);
+    out[j * 5 + 2] = T(ref85x4[j * 4 + 3]);
+    out[j * 5 + 3] = T(sin(ref85x4[j * 4 + 3]));
+    out[j * 5 + 4] = T(cos(ref85x4[j * 4 + 3]));
+  }
+}
+
+template <typename T>
+static void run_solve(const SolverConfig& cfg, const double* ref, const HsBatch& b, int B, float* actions,
+                      int* status, int* iters, float* cost, float* U_out, int* outer_out) {
+  std::vector<T> rt;
+  make_ref(ref, rt);
+  std::vector<T> buf(slots_per_problem(cfg.N, cfg.M));
+  for (int i = 0; i < B; ++i) {
+    Slots<T> sl{buf.data(), 1, cfg.N, cfg.M};
+    ProblemScalars<T> p;
+    load_problem(b, B, i, cfg, p, sl);
+    SolveState<T> s;
+    solve_one(cfg, p, rt.data(), sl, s);
+    actions[2 * i] = float(sl.U(0, 0));
+    actions[2 * i + 1] = float(sl.U(0, 1));
+    status[i] = s.status;
+    iters[i] = s.iter;
+    if (outer_out) outer_out[i] = 0;
+    cost[i] = float(s.J);
+    if (U_out)
+      for (int k = 0; k < cfg.N; ++k) { U_out[((size_t)i * cfg.N + k) * 2] = float(sl.U(k, 0)); U_out[((size_t)i * cfg.N + k) * 2 + 1] = float(sl.U(k, 1)); }
+  }
+}
+
+template <typename T>
+static void run_rollout_cost(const SolverConfig& cfg, const double* ref, const HsBatch& b, int B, const float* U,
+                             const float* ref_v /*[N][B] or null*/, float* X_out, float* cost6, float* total) {
+  std::vector<T> rt;
+  make_ref(ref, rt);
+  std::vector<T> buf(slots_per_problem(cfg.N, cfg.M));
+  for (int i = 0; i < B; ++i) {
+    Slots<T> sl{buf.data(), 1, cfg.N, cfg.M};
+    ProblemScalars<T> p;
+    load_problem(b, B, i, cfg, p, sl);
+    for (int k = 0; k < cfg.N; ++k) {
+      sl.U(k, 0) = T(U[((size_t)i * cfg.N + k) * 2]);
+      sl.U(k, 1) = T(U[((size_t)i * cfg.N + k) * 2 + 1]);
+    }
+    (void)ref_v;
+    T comp[6] = {0, 0, 0, 0, 0, 0};
+    T J = rollout_nominal(cfg, p, rt.data(), sl, comp);
+    // final_state component (pure_mpc.py:195-202), reported never optimised
+    int Jn = p.ego_index + cfg.N;
+    Jn = Jn < kNRef - 1 ? Jn : kNRef - 1;
+    const T* r = rt.data() + Jn * kRefStride;
+    T ex = sl.X(cfg.N, 0) - r[0], ey = sl.X(cfg.N, 1) + r[1];
+    T ev = sl.X(cfg.N, 3) - ref_speed_at(p, cfg.N), eth = sl.X(cfg.N, 2) - r[2];
+    comp[2] = T(100) * (ex * ex + ey * ey + T(20) * ev * ev + eth * eth);
+    for (int c = 0; c < 6; ++c) cost6[(size_t)i * 6 + c] = float(comp[c]);
+    total[i] = float(J);
+    for (int k = 0; k <= cfg.N; ++k)
+      for (int c = 0; c < 4; ++c) X_out[((size_t)i * (cfg.N + 1) + k) * 4 + c] = float(sl.X(k, c));
+  }
+}
+
+extern "C" {
+
+int hs_solve(const SolverConfig* cfg, const double* ref85x4, const HsBatch* b, int B, int use_double, float* actions,
+             int* status, int* iters, float* cost, float* U_out, int* outer_out) {
+  if (use_double) run_solve<double>(*cfg, ref85x4, *b, B, actions, status, iters, cost, U_out, outer_out);
+  else run_solve<float>(*cfg, ref85x4, *b, B, actions, status, iters, cost, U_out, outer_out);
+  return 0;
+}
+
+int hs_rollout_cost(const SolverConfig* cfg, const double* ref85x4, const HsBatch* b, int B, int use_double,
+                    const float* U, float* X_out, float* cost6, float* total) {
+  if (use_double) run_rollout_cost<double>(*cfg, ref85x4, *b, B, U, nullptr, X_out, cost6, total);
+  else run_rollout_cost<float>(*cfg, ref85x4, *b, B, U, nullptr, X_out, cost6, total);
+  return 0;
+}
+
+int hs_sizeof_config() { return (int)sizeof(SolverConfig); }
+}
+
+// debugging aid: model-vs-actual merit along the DDP step from a given nominal U
+extern "C" int hs_linesearch_probe(const SolverConfig* cfg, const double* ref, const HsBatch* b, int B, int i, const float* U,
+                                   double mu, int n_alpha, const double* alphas, double* out /* J0,d1,d2,J(a)... */) {
+  std::vector<double> rt;
+  make_ref(ref, rt);
+  std::vector<double> buf(slots_per_problem(cfg->N, cfg->M));
+  Slots<double> sl{buf.data(), 1, cfg->N, cfg->M};
+  ProblemScalars<double> p;
+  load_problem(*b, B, i, *cfg, p, sl);
+  for (int k = 0; k < cfg->N; ++k) { sl.U(k, 0) = U[2 * k]; sl.U(k, 1) = U[2 * k + 1]; }
+  out[0] = rollout_nominal(*cfg, p, rt.data(), sl, (double*)nullptr);
+  backward_pass(*cfg, p, rt.data(), sl, mu, 1.0, &out[1], &out[2]);
+  for (int a = 0; a < n_alpha; ++a) { double md; out[3 + a] = forward_pass<double, false>(*cfg, p, rt.data(), sl, alphas[a], &md); }
+  for (int k = 0; k < cfg->N; ++k) { out[3 + n_alpha + 2 * k] = sl.F(k, 0); out[3 + n_alpha + 2 * k + 1] = sl.F(k, 1); }
+  return 0;
+}
