@@ -1,0 +1,371 @@
+// mpc_capi.cu -- extern "C" boundary of libmpcb200.so (see include/mpc_b200.h).
+// Host side only: argument checks, workspace ownership, launch sequencing, error text.
+// No exception crosses the ABI; there is no CPU compute path anywhere in this library.
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "mpc_internal.h"
+
+using namespace mpcb;
+
+static thread_local std::string g_create_error;
+
+struct MpcHandle {
+  MpcConfig cfg;
+  SolverConfig scfg;
+  int device = 0;
+  int max_batch = 0;
+  int sm_count = 0, cc_major = 0, cc_minor = 0, smem_optin = 0;
+  int tpb = 0, grid = 0;
+  size_t smem = 0;
+  // device workspace
+  void* ws_block = nullptr;       // one allocation carved into the BatchWs arrays
+  BatchWs ws{};
+  int* work_counter = nullptr;
+  float* sink = nullptr;
+  // host-call staging (mpc_predict_host)
+  float* d_obs = nullptr; float* d_ref_speed = nullptr; float* d_weights = nullptr; uint8_t* d_reset = nullptr;
+  float* d_actions = nullptr; int32_t* d_status = nullptr; int32_t* d_iters = nullptr; float* d_cost = nullptr;
+  int32_t* d_mem = nullptr; int32_t* d_memo = nullptr; uint8_t* d_iscol = nullptr;
+  cudaStream_t host_stream = nullptr;
+  // measurement
+  int64_t launches = 0;
+  bool timing = false;
+  std::vector<cudaEvent_t> ev_prepare, ev_solve;   // start/stop pairs
+  std::string err;
+};
+
+static int fail(MpcHandle* h, int code, const char* what, cudaError_t e = cudaSuccess) {
+  char buf[512];
+  if (e != cudaSuccess) snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+  else snprintf(buf, sizeof buf, "%s", what);
+  if (h) h->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CK(h, call)                                                    \
+  do {                                                                 \
+    cudaError_t e__ = (call);                                          \
+    if (e__ != cudaSuccess) return fail((h), MPC_ERR_CUDA, #call, e__); \
+  } while (0)
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+extern "C" {
+
+MPC_API const char* mpc_last_error(const MpcHandle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+MPC_API int mpc_destroy(MpcHandle* h) {
+  if (!h) return MPC_OK;
+  cudaSetDevice(h->device);
+  for (auto e : h->ev_prepare) cudaEventDestroy(e);
+  for (auto e : h->ev_solve) cudaEventDestroy(e);
+  cudaFree(h->ws_block); cudaFree(h->work_counter); cudaFree(h->sink);
+  cudaFree(h->d_obs); cudaFree(h->d_ref_speed); cudaFree(h->d_weights); cudaFree(h->d_reset);
+  cudaFree(h->d_actions); cudaFree(h->d_status); cudaFree(h->d_iters); cudaFree(h->d_cost);
+  cudaFree(h->d_mem); cudaFree(h->d_memo); cudaFree(h->d_iscol);
+  if (h->host_stream) cudaStreamDestroy(h->host_stream);
+  delete h;
+  return MPC_OK;
+}
+
+MPC_API int mpc_create(const MpcConfig* cfg, int device, int max_batch, MpcHandle** out) {
+  if (!cfg || !out) return fail(nullptr, MPC_ERR_BAD_ARG, "mpc_create: null argument");
+  *out = nullptr;
+  if (cfg->abi_version != MPC_ABI_VERSION) return fail(nullptr, MPC_ERR_BAD_ARG, "mpc_create: abi_version mismatch");
+  if (cfg->horizon < 2 || cfg->horizon > 64) return fail(nullptr, MPC_ERR_BAD_ARG, "mpc_create: horizon must be in 2..64");
+  if (cfg->vehicles_count < 1 || cfg->vehicles_count - 1 > MPC_MAX_OBSTACLES)
+    return fail(nullptr, MPC_ERR_BAD_ARG, "mpc_create: vehicles_count must be in 1..17");
+  if (!(cfg->dt > 0.f)) return fail(nullptr, MPC_ERR_BAD_ARG, "mpc_create: dt must be positive");
+  if (max_batch < 1) return fail(nullptr, MPC_ERR_BAD_ARG, "mpc_create: max_batch must be >= 1");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+    return fail(nullptr, MPC_ERR_NO_DEVICE, "mpc_create: no CUDA device (this library has no CPU path)");
+  if (device < 0 || device >= ndev) return fail(nullptr, MPC_ERR_BAD_ARG, "mpc_create: device index out of range");
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(nullptr, MPC_ERR_NO_DEVICE, "mpc_create: cannot query device");
+  if (prop.major != 10) return fail(nullptr, MPC_ERR_NO_DEVICE, "mpc_create: device is not sm_100 (B200); the kernels are built for sm_100a only");
+
+  MpcHandle* h = new (std::nothrow) MpcHandle();
+  if (!h) return fail(nullptr, MPC_ERR_CUDA, "mpc_create: out of host memory");
+  h->cfg = *cfg;
+  h->device = device;
+  h->max_batch = max_batch;
+  h->sm_count = prop.multiProcessorCount;
+  h->cc_major = prop.major; h->cc_minor = prop.minor;
+  h->smem_optin = (int)prop.sharedMemPerBlockOptin;
+  const int N = cfg->horizon, M = cfg->vehicles_count - 1;
+  SolverConfig& s = h->scfg;
+  s.N = N; s.M = M; s.dt = cfg->dt;
+  s.w_distance = cfg->weight_distance; s.w_collision = cfg->weight_collision;
+  s.literal_no_collision = cfg->literal_no_collision;
+  s.max_iter = cfg->max_iter > 0 ? cfg->max_iter : 60;
+  s.tol_step = cfg->tol_step > 0.f ? cfg->tol_step : 1e-4f;
+  s.reg_min = cfg->reg_min > 0.f ? cfg->reg_min : 1e-2f;
+
+#define CKC(call)                                                                        \
+  do {                                                                                   \
+    cudaError_t e__ = (call);                                                            \
+    if (e__ != cudaSuccess) { fail(nullptr, MPC_ERR_CUDA, #call, e__); mpc_destroy(h); return MPC_ERR_CUDA; } \
+  } while (0)
+
+  CKC(cudaSetDevice(device));
+  // grid / block: as many problems resident per SM as the slot file allows
+  int tpb = cfg->threads_per_block > 0 ? cfg->threads_per_block : 128;
+  tpb = (tpb + 31) / 32 * 32;
+  if (tpb > 128) tpb = 128;
+  while (tpb > 32 && solve_smem_bytes(N, M, tpb) > (size_t)h->smem_optin) tpb -= 32;
+  if (solve_smem_bytes(N, M, tpb) > (size_t)h->smem_optin) { fail(nullptr, MPC_ERR_BAD_ARG, "mpc_create: horizon/obstacle count do not fit shared memory"); mpc_destroy(h); return MPC_ERR_BAD_ARG; }
+  h->tpb = tpb;
+  h->smem = solve_smem_bytes(N, M, tpb);
+  int bps = cfg->blocks_per_sm > 0 ? cfg->blocks_per_sm : (int)((size_t)prop.sharedMemPerMultiprocessor / (h->smem + 1024));
+  if (bps < 1) bps = 1;
+  h->grid = h->sm_count * bps;
+  CKC(configure_solve_kernel(h->smem));
+  CKC(upload_ref_table_solve());
+  CKC(upload_ref_table_prepare());
+
+  // parsed-problem workspace
+  const size_t B = (size_t)max_batch;
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  size_t o_s0 = carve(4 * B * 4), o_ei = carve(B * 4), o_ws = carve(B * 4), o_wc = carve(B * 4), o_wd = carve(B * 4);
+  size_t o_va = carve(B * 4), o_vs = carve(B * 4), o_vb = carve(B * 4), o_vn = carve(B * 4), o_ic = carve(B), o_no = carve(B * 4);
+  size_t o_ob = carve((size_t)(M > 0 ? M : 1) * 4 * B * 4);
+  CKC(cudaMalloc(&h->ws_block, off));
+  CKC(cudaMemset(h->ws_block, 0, off));
+  char* base = (char*)h->ws_block;
+  h->ws.s0 = (float*)(base + o_s0); h->ws.ego_index = (int32_t*)(base + o_ei); h->ws.w_speed = (float*)(base + o_ws);
+  h->ws.w_control = (float*)(base + o_wc); h->ws.w_diff = (float*)(base + o_wd); h->ws.vr_a = (float*)(base + o_va);
+  h->ws.vr_slope = (float*)(base + o_vs); h->ws.vr_b = (float*)(base + o_vb); h->ws.vr_n = (int32_t*)(base + o_vn);
+  h->ws.is_collide = (uint8_t*)(base + o_ic); h->ws.n_obs = (int32_t*)(base + o_no); h->ws.obstacles = (float*)(base + o_ob);
+  CKC(cudaMalloc(&h->work_counter, sizeof(int)));
+  CKC(cudaMalloc(&h->sink, 256));
+  // staging for the host-buffer entry point
+  CKC(cudaMalloc(&h->d_obs, B * cfg->vehicles_count * 8 * 4));
+  CKC(cudaMalloc(&h->d_ref_speed, B * 4));
+  CKC(cudaMalloc(&h->d_weights, B * 3 * 4));
+  CKC(cudaMalloc(&h->d_reset, B));
+  CKC(cudaMalloc(&h->d_actions, B * 2 * 4));
+  CKC(cudaMalloc(&h->d_status, B * 4));
+  CKC(cudaMalloc(&h->d_iters, B * 4));
+  CKC(cudaMalloc(&h->d_cost, B * 4));
+  CKC(cudaMalloc(&h->d_mem, B * 4));
+  CKC(cudaMalloc(&h->d_memo, B * 4));
+  CKC(cudaMalloc(&h->d_iscol, B));
+  CKC(cudaMemset(h->d_mem, 0, B * 4));
+  CKC(cudaMemset(h->d_memo, 0xff, B * 4));
+  CKC(cudaMemset(h->d_iscol, 0, B));
+  CKC(cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking));
+  CKC(cudaDeviceSynchronize());
+#undef CKC
+  *out = h;
+  return MPC_OK;
+}
+
+MPC_API int mpc_device_info(const MpcHandle* h, int* sm_count, int* cc_major, int* cc_minor, int* smem_per_block_optin) {
+  if (!h) return MPC_ERR_BAD_ARG;
+  if (sm_count) *sm_count = h->sm_count;
+  if (cc_major) *cc_major = h->cc_major;
+  if (cc_minor) *cc_minor = h->cc_minor;
+  if (smem_per_block_optin) *smem_per_block_optin = h->smem_optin;
+  return MPC_OK;
+}
+
+MPC_API int mpc_workspace_batch(MpcHandle* h, MpcProblemBatch* out) {
+  if (!h || !out) return MPC_ERR_BAD_ARG;
+  out->s0 = h->ws.s0; out->ego_index = h->ws.ego_index; out->w_speed = h->ws.w_speed; out->w_control = h->ws.w_control;
+  out->w_diff = h->ws.w_diff; out->vr_a = h->ws.vr_a; out->vr_slope = h->ws.vr_slope; out->vr_b = h->ws.vr_b;
+  out->vr_n = h->ws.vr_n; out->is_collide = h->ws.is_collide; out->n_obs = h->ws.n_obs; out->obstacles = h->ws.obstacles;
+  return MPC_OK;
+}
+
+static int check_batch(MpcHandle* h, const MpcProblemBatch* b, int B) {
+  if (!h) return MPC_ERR_BAD_ARG;
+  if (!b || B < 0) return fail(h, MPC_ERR_BAD_ARG, "null batch or negative size");
+  if (!b->s0 || !b->ego_index || !b->w_speed || !b->w_control || !b->w_diff || !b->vr_a || !b->vr_slope || !b->vr_b || !b->vr_n)
+    return fail(h, MPC_ERR_BAD_ARG, "MpcProblemBatch: a required array is null");
+  if (h->scfg.M > 0 && h->scfg.w_distance != 0.f && (!b->obstacles || !b->n_obs))
+    return fail(h, MPC_ERR_BAD_ARG, "MpcProblemBatch: obstacles/n_obs required when weight_distance != 0");
+  return MPC_OK;
+}
+
+MPC_API int mpc_rollout_cost(MpcHandle* h, const MpcProblemBatch* batch, int B, const float* U, float* X_out, float* cost6_out,
+                     float* total_out, void* stream) {
+  int rc = check_batch(h, batch, B);
+  if (rc) return rc;
+  if (!U || !X_out || !cost6_out || !total_out) return fail(h, MPC_ERR_BAD_ARG, "mpc_rollout_cost: null output/input");
+  if (B == 0) return MPC_OK;
+  CK(h, cudaSetDevice(h->device));
+  CK(h, launch_rollout_cost(h->scfg, *batch, B, U, X_out, cost6_out, total_out, (cudaStream_t)stream));
+  h->launches += 1;
+  return MPC_OK;
+}
+
+static int timed_begin(MpcHandle* h, std::vector<cudaEvent_t>& v, cudaStream_t st) {
+  if (!h->timing) return MPC_OK;
+  cudaEvent_t a, b;
+  CK(h, cudaEventCreate(&a));
+  CK(h, cudaEventCreate(&b));
+  v.push_back(a); v.push_back(b);
+  CK(h, cudaEventRecord(a, st));
+  return MPC_OK;
+}
+static int timed_end(MpcHandle* h, std::vector<cudaEvent_t>& v, cudaStream_t st) {
+  if (!h->timing) return MPC_OK;
+  CK(h, cudaEventRecord(v.back(), st));
+  return MPC_OK;
+}
+
+MPC_API int mpc_solve(MpcHandle* h, const MpcProblemBatch* batch, int B, const MpcSolveOut* out, void* stream) {
+  int rc = check_batch(h, batch, B);
+  if (rc) return rc;
+  if (!out || !out->actions) return fail(h, MPC_ERR_BAD_ARG, "mpc_solve: actions output is required");
+  if (B == 0) return MPC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(h, cudaSetDevice(h->device));
+  CK(h, cudaMemsetAsync(h->work_counter, 0, sizeof(int), st));
+  SolveLaunch s;
+  s.cfg = h->scfg; s.batch = *batch; s.out = *out; s.B = B; s.work_counter = h->work_counter;
+  s.threads_per_block = h->tpb; s.smem_bytes = h->smem;
+  int need = (B + h->tpb - 1) / h->tpb;
+  s.grid = need < h->grid ? need : h->grid;
+  if ((rc = timed_begin(h, h->ev_solve, st))) return rc;
+  CK(h, launch_solve(s, st));
+  if ((rc = timed_end(h, h->ev_solve, st))) return rc;
+  h->launches += 1;
+  return MPC_OK;
+}
+
+MPC_API int mpc_prepare(MpcHandle* h, const float* obs, const float* ref_speed, const float* weights, const uint8_t* reset_mask,
+                const MpcLatchState* latch, int B, const MpcCollisionOut* col, void* stream) {
+  if (!h) return MPC_ERR_BAD_ARG;
+  if (!obs || B < 0) return fail(h, MPC_ERR_BAD_ARG, "mpc_prepare: obs is null or B < 0");
+  if (B > h->max_batch) return fail(h, MPC_ERR_TOO_LARGE, "mpc_prepare: B exceeds max_batch of mpc_create");
+  if (h->cfg.collision_check && (!latch || !latch->collision_memory || !latch->memo_conflict || !latch->is_collide))
+    return fail(h, MPC_ERR_BAD_ARG, "mpc_prepare: latch state is required when collision_check is on");
+  if (B == 0) return MPC_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(h, cudaSetDevice(h->device));
+  PrepareParams p{};
+  p.obs = obs; p.ref_speed = ref_speed; p.weights = weights; p.reset_mask = reset_mask;
+  if (latch) p.latch = *latch;
+  if (col) p.col = *col;
+  p.ws = h->ws;
+  p.B = B; p.V = h->cfg.vehicles_count; p.M = h->scfg.M; p.N = h->scfg.N;
+  // dt arrives as float (0.1f); the reference's dt is the double 1/policy_frequency
+  p.dt = 1.0 / (double)(long long)(1.0 / (double)h->cfg.dt + 0.5) ;
+  p.w_speed = h->cfg.weight_speed; p.w_control = h->cfg.weight_control; p.w_diff = h->cfg.weight_input_diff;
+  p.collision_check = h->cfg.collision_check;
+  int rc;
+  if ((rc = timed_begin(h, h->ev_prepare, st))) return rc;
+  CK(h, launch_prepare(p, st));
+  if ((rc = timed_end(h, h->ev_prepare, st))) return rc;
+  h->launches += 1;
+  return MPC_OK;
+}
+
+MPC_API int mpc_predict(MpcHandle* h, const float* obs, const float* ref_speed, const float* weights, const uint8_t* reset_mask,
+                const MpcLatchState* latch, int B, const MpcSolveOut* out, const MpcCollisionOut* col, void* stream) {
+  int rc = mpc_prepare(h, obs, ref_speed, weights, reset_mask, latch, B, col, stream);
+  if (rc) return rc;
+  MpcProblemBatch b;
+  mpc_workspace_batch(h, &b);
+  return mpc_solve(h, &b, B, out, stream);
+}
+
+MPC_API int mpc_predict_host(MpcHandle* h, const float* obs_host, const float* ref_speed_host, const float* weights_host,
+                     const uint8_t* reset_mask_host, int B, float* actions_host, int32_t* status_host,
+                     uint8_t* is_collide_host, int64_t* h2d_bytes, int64_t* d2h_bytes) {
+  if (!h) return MPC_ERR_BAD_ARG;
+  if (!obs_host || !actions_host || B < 0) return fail(h, MPC_ERR_BAD_ARG, "mpc_predict_host: null obs/actions or B < 0");
+  if (B > h->max_batch) return fail(h, MPC_ERR_TOO_LARGE, "mpc_predict_host: B exceeds max_batch of mpc_create");
+  if (B == 0) return MPC_OK;
+  CK(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->host_stream;
+  int64_t up = 0, down = 0;
+  const size_t nobs = (size_t)B * h->cfg.vehicles_count * 8 * 4;
+  CK(h, cudaMemcpyAsync(h->d_obs, obs_host, nobs, cudaMemcpyHostToDevice, st)); up += nobs;
+  if (ref_speed_host) { CK(h, cudaMemcpyAsync(h->d_ref_speed, ref_speed_host, (size_t)B * 4, cudaMemcpyHostToDevice, st)); up += (int64_t)B * 4; }
+  if (weights_host) { CK(h, cudaMemcpyAsync(h->d_weights, weights_host, (size_t)B * 12, cudaMemcpyHostToDevice, st)); up += (int64_t)B * 12; }
+  if (reset_mask_host) { CK(h, cudaMemcpyAsync(h->d_reset, reset_mask_host, (size_t)B, cudaMemcpyHostToDevice, st)); up += B; }
+  MpcLatchState latch{h->d_mem, h->d_memo, h->d_iscol};
+  MpcSolveOut out{h->d_actions, h->d_status, h->d_iters, h->d_cost, nullptr};
+  MpcCollisionOut col{};
+  int rc = mpc_predict(h, h->d_obs, ref_speed_host ? h->d_ref_speed : nullptr, weights_host ? h->d_weights : nullptr,
+                       reset_mask_host ? h->d_reset : nullptr, &latch, B, &out, &col, st);
+  if (rc) return rc;
+  CK(h, cudaMemcpyAsync(actions_host, h->d_actions, (size_t)B * 8, cudaMemcpyDeviceToHost, st)); down += (int64_t)B * 8;
+  if (status_host) { CK(h, cudaMemcpyAsync(status_host, h->d_status, (size_t)B * 4, cudaMemcpyDeviceToHost, st)); down += (int64_t)B * 4; }
+  if (is_collide_host) { CK(h, cudaMemcpyAsync(is_collide_host, h->ws.is_collide, (size_t)B, cudaMemcpyDeviceToHost, st)); down += B; }
+  CK(h, cudaStreamSynchronize(st));
+  if (h2d_bytes) *h2d_bytes = up;
+  if (d2h_bytes) *d2h_bytes = down;
+  return MPC_OK;
+}
+
+MPC_API int64_t mpc_launch_count(const MpcHandle* h) { return h ? h->launches : 0; }
+
+MPC_API int mpc_fp32_peak(MpcHandle* h, int repeats, float* tflops_out) {
+  if (!h || !tflops_out) return MPC_ERR_BAD_ARG;
+  CK(h, cudaSetDevice(h->device));
+  const int block = 256, grid = h->sm_count * 8, iters = 4096;
+  cudaEvent_t a, b;
+  CK(h, cudaEventCreate(&a));
+  CK(h, cudaEventCreate(&b));
+  CK(h, launch_fma_peak(h->sink, 64, grid, block, nullptr));   // warm-up
+  float best = 0.f;
+  if (repeats < 1) repeats = 1;
+  for (int r = 0; r < repeats; ++r) {
+    CK(h, cudaEventRecord(a, nullptr));
+    CK(h, launch_fma_peak(h->sink, iters, grid, block, nullptr));
+    CK(h, cudaEventRecord(b, nullptr));
+    CK(h, cudaEventSynchronize(b));
+    float ms = 0.f;
+    CK(h, cudaEventElapsedTime(&ms, a, b));
+    const double flops = 2.0 * 16 * 8 * (double)iters * (double)grid * block;
+    const float tf = (float)(flops / (ms * 1e-3) / 1e12);
+    if (tf > best) best = tf;
+    h->launches += 1;
+  }
+  h->launches += 1;
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  *tflops_out = best;
+  return MPC_OK;
+}
+
+MPC_API int mpc_timing_begin(MpcHandle* h) {
+  if (!h) return MPC_ERR_BAD_ARG;
+  for (auto e : h->ev_prepare) cudaEventDestroy(e);
+  for (auto e : h->ev_solve) cudaEventDestroy(e);
+  h->ev_prepare.clear(); h->ev_solve.clear();
+  h->timing = true;
+  return MPC_OK;
+}
+
+MPC_API int mpc_timing_end(MpcHandle* h, float* prepare_ms_avg, float* solve_ms_avg, int* n_prepare, int* n_solve) {
+  if (!h) return MPC_ERR_BAD_ARG;
+  h->timing = false;
+  CK(h, cudaSetDevice(h->device));
+  CK(h, cudaDeviceSynchronize());
+  auto avg = [&](std::vector<cudaEvent_t>& v, float* out_ms, int* out_n) -> int {
+    double tot = 0; int n = 0;
+    for (size_t i = 0; i + 1 < v.size(); i += 2) {
+      float ms = 0.f;
+      cudaError_t e = cudaEventElapsedTime(&ms, v[i], v[i + 1]);
+      if (e != cudaSuccess) return fail(h, MPC_ERR_CUDA, "cudaEventElapsedTime", e);
+      tot += ms; ++n;
+    }
+    if (out_ms) *out_ms = n ? (float)(tot / n) : 0.f;
+    if (out_n) *out_n = n;
+    return MPC_OK;
+  };
+  int rc = avg(h->ev_prepare, prepare_ms_avg, n_prepare);
+  if (rc) return rc;
+  return avg(h->ev_solve, solve_ms_avg, n_solve);
+}
+
+}  // extern "C"

@@ -1,0 +1,65 @@
+// Internal (not installed) declarations shared by the translation units of libmpcb200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mpc_b200.h"
+#include "mpc_core.cuh"
+
+namespace mpcb {
+
+// mutable view of the handle's parsed-problem workspace (same layout as MpcProblemBatch)
+struct BatchWs {
+  float* s0;
+  int32_t* ego_index;
+  float* w_speed;
+  float* w_control;
+  float* w_diff;
+  float* vr_a;
+  float* vr_slope;
+  float* vr_b;
+  int32_t* vr_n;
+  uint8_t* is_collide;
+  int32_t* n_obs;
+  float* obstacles;
+};
+
+struct PrepareParams {
+  const float* obs;            // [B][V][8]
+  const float* ref_speed;      // [B] or null (NaN = none)
+  const float* weights;        // [B][3] or null
+  const uint8_t* reset_mask;   // [B] or null
+  MpcLatchState latch;         // pointers may be null when collision_check == 0
+  MpcCollisionOut col;         // any pointer may be null
+  BatchWs ws;
+  int B, V, M, N;
+  double dt;
+  float w_speed, w_control, w_diff;
+  int collision_check;
+};
+
+// launches (defined in mpc_prepare.cu, compiled with -fmad=false so that FP64 results are
+// bit-identical to the numpy oracle's un-fused arithmetic)
+cudaError_t launch_prepare(const PrepareParams& p, cudaStream_t stream);
+cudaError_t upload_ref_table_prepare();
+
+// defined in mpc_solve.cu
+struct SolveLaunch {
+  SolverConfig cfg;
+  MpcProblemBatch batch;
+  MpcSolveOut out;
+  int B;
+  int* work_counter;      // device, zeroed before launch
+  int threads_per_block;
+  int grid;
+  size_t smem_bytes;
+};
+cudaError_t configure_solve_kernel(size_t smem_bytes);
+cudaError_t launch_solve(const SolveLaunch& s, cudaStream_t stream);
+cudaError_t launch_rollout_cost(const SolverConfig& cfg, const MpcProblemBatch& batch, int B, const float* U,
+                                float* X_out, float* cost6, float* total, cudaStream_t stream);
+cudaError_t upload_ref_table_solve();
+cudaError_t launch_fma_peak(float* sink, int iters, int grid, int block, cudaStream_t stream);
+size_t solve_smem_bytes(int N, int M, int tpb);
+
+}  // namespace mpcb

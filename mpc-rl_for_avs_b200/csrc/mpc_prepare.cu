@@ -1,0 +1,331 @@
+// mpc_prepare.cu -- observation parsing, collision prediction, latch, reference-speed regeneration.
+// COMPILED WITH -fmad=false: everything that decides a flag or an index is FP64 with the same
+// un-fused operation order as the numpy oracle, so flags and indices are bit-exact.
+//
+// Replaces (reference file:line):
+//   Agent._parse_obs                      agents/base_agent.py:81-116
+//   nearest reference row                 agents/pure_mpc.py:106-109, 566-570
+//   predict_ego_future_positions          agents/pure_mpc.py:459-527
+//   predict_future_positions              agents/pure_mpc.py:529-550
+//   _check_collision (latch + detection)  agents/pure_mpc.py:552-676
+//   update_reference_states               agents/pure_mpc.py:678-724
+//
+// Mapping: 8 (or 16) lanes per environment; lane m owns other-vehicle m.  The ego's predicted
+// polyline (<= 31 FP64 points) is built cooperatively into shared memory, each lane then tests
+// its vehicle's straight 31-point track against it.  Flags / earliest conflict row are combined
+// with sub-warp shuffles, lane 0 of the group updates the latch and writes the solve descriptor.
+#include "mpc_internal.h"
+
+#include "ref_table.inc"
+
+namespace mpcb {
+
+constexpr int kPred = 30;            // PREDICTION_HORIZON, agents/pure_mpc.py:554
+constexpr int kTimeThreshold = 30;   // TIME_THRESHOLD,     agents/pure_mpc.py:555
+constexpr int kSafetyBuffer = 5;     // SAFETY_BUFFER_POINTS, agents/pure_mpc.py:681
+constexpr int kMemorySteps = 10;     // collision_memory_steps, agents/pure_mpc.py:39
+constexpr double kMaxAccPred = 3.5;  // Vehicle.max_acceleration, agents/utils.py:39
+constexpr double kPi = 3.141592653589793;
+
+__constant__ double c_refd[kNRef][4];     // x, y, v, heading
+__constant__ double c_seg[kNRef - 1];     // |ref[j+1] - ref[j]|
+
+cudaError_t upload_ref_table_prepare() {
+  cudaError_t e = cudaMemcpyToSymbol(c_refd, kRefPath, sizeof(kRefPath));
+  if (e != cudaSuccess) return e;
+  double seg[kNRef - 1];
+  for (int j = 0; j < kNRef - 1; ++j) {
+    double dx = kRefPath[j + 1][0] - kRefPath[j][0], dy = kRefPath[j + 1][1] - kRefPath[j][1];
+    volatile double xx = dx * dx, yy = dy * dy;     // volatile: no host-side FMA contraction either
+    seg[j] = sqrt(xx + yy);
+  }
+  return cudaMemcpyToSymbol(c_seg, seg, sizeof(seg));
+}
+
+__device__ __forceinline__ double norm2(double dx, double dy) { return sqrt(dx * dx + dy * dy); }
+__device__ __forceinline__ double orient(double ax, double ay, double bx, double by, double cx, double cy) {
+  return (bx - ax) * (cy - ay) - (by - ay) * (cx - ax);
+}
+
+template <int LPP>
+__global__ void __launch_bounds__(256)
+k_prepare(const PrepareParams P) {
+  constexpr int PPB = 256 / LPP;                      // environments per block
+  __shared__ double s_ex[PPB][kPred + 1];
+  __shared__ double s_ey[PPB][kPred + 1];
+  const int g = threadIdx.x / LPP;                    // group inside the block
+  const int l = threadIdx.x % LPP;                    // lane inside the group
+  const int b = blockIdx.x * PPB + g;
+  const bool live = b < P.B;
+  const int bb = live ? b : P.B - 1;                  // dead groups shadow the last env (no stores)
+  const unsigned gmask = (LPP == 32) ? 0xffffffffu : (((1u << LPP) - 1u) << ((threadIdx.x % 32) / LPP * LPP));
+  const float* ob = P.obs + (size_t)bb * P.V * 8;
+
+  // ---- _parse_obs: ego row, number of present others --------------------------------------
+  const double ex = ob[1], ey = ob[2];
+  const double evx = ob[3], evy = ob[4];
+  double eth = ob[5];
+  while (eth > kPi) eth -= 2 * kPi;                   // base_agent.py:156-170
+  while (eth < -kPi) eth += 2 * kPi;
+  const double ev = norm2(evx, evy);                  // agents/utils.py:36
+  int present = 0;
+  for (int r = 0; r < P.V; ++r) present += (ob[r * 8] == 1.0f) ? 1 : 0;
+  int n_obs = present - 1;
+  n_obs = n_obs < 0 ? 0 : (n_obs > P.M ? P.M : n_obs);
+
+  // ---- nearest reference row: global argmin, first minimum wins ---------------------------
+  double bd = 1e300;
+  int bj = 0;
+  for (int j = l; j < kNRef; j += LPP) {
+    double d = norm2(ex - c_refd[j][0], ey - c_refd[j][1]);
+    if (d < bd) { bd = d; bj = j; }
+  }
+#pragma unroll
+  for (int o = LPP / 2; o > 0; o >>= 1) {
+    double od = __shfl_xor_sync(gmask, bd, o, LPP);
+    int oj = __shfl_xor_sync(gmask, bj, o, LPP);
+    if (od < bd || (od == bd && oj < bj)) { bd = od; bj = oj; }
+  }
+  const int ego_index = bj;
+
+  // ---- this lane's other vehicle ---------------------------------------------------------------
+  const bool has_veh = l < n_obs;
+  double ox = 0, oy = 0, incx = 0, incy = 0;
+  if (has_veh) {
+    const float* r = ob + (size_t)(l + 1) * 8;
+    ox = r[1]; oy = r[2];
+    const double sp = norm2((double)r[3], (double)r[4]);
+    const double hd = r[5];                            // NOT wrapped, base_agent.py:112
+    const double sd = sp * P.dt;                       // speed * dt * (cos, sin), base_agent.py:172-174
+    incx = sd * cos(hd);
+    incy = sd * sin(hd);
+  }
+
+  // ---- latch (agents/pure_mpc.py:558-563) -----------------------------------------------------
+  int mem = 0, memo = -1;
+  int is_col = 0;
+  if (P.collision_check) {
+    mem = P.latch.collision_memory[bb];
+    memo = P.latch.memo_conflict[bb];
+    is_col = P.latch.is_collide[bb];
+    if (P.reset_mask && P.reset_mask[bb]) { mem = 0; memo = -1; is_col = 0; }
+  }
+  const bool latched = P.collision_check && mem > 0 && memo >= 0;
+  int my_flag = 0, my_cidx = -1, my_deg = 0;
+  int cmin = -1;
+  int stop_index = -1;
+  bool aborted = false;
+
+  if (P.collision_check && !latched) {
+    // ---- ego polyline: arc length along the reference from ego_index -------------------------
+    const int len = kNRef - ego_index;                 // points of reference_trajectory[start:]
+    int n_valid = 0;                                   // how many of t = 1..30 produce a point
+    if (len >= 2) {
+      const double vref = c_refd[ego_index][2];
+      for (int t = 1 + l; t <= kPred; t += LPP) {
+        double cur = ev, dist = 0.0;
+        for (int i = 1; i <= t; ++i) {                 // same sequential sums as the reference
+          if (cur < vref) { double nv = cur + kMaxAccPred * P.dt; cur = nv < vref ? nv : vref; }
+          else cur = vref;
+          dist += cur * P.dt;
+        }
+        // left searchsorted over cum[0..len-1], cum[0] = 0, cum[i] = cum[i-1] + seg[start+i-1]
+        int idx = 0;
+        double cum = 0.0, prev = 0.0;
+        while (cum < dist) {
+          ++idx;
+          if (idx >= len) break;
+          prev = cum;
+          cum = cum + c_seg[ego_index + idx - 1];
+        }
+        if (idx >= len) continue;                       // past the end of the path: no point
+        double px, py;
+        if (idx == 0) { px = c_refd[ego_index][0]; py = c_refd[ego_index][1]; }
+        else {
+          double alpha = (cum != prev) ? (dist - prev) / (cum - prev) : 1.0;
+          alpha = alpha < 0.0 ? 0.0 : (alpha > 1.0 ? 1.0 : alpha);
+          const double ax = c_refd[ego_index + idx - 1][0], ay = c_refd[ego_index + idx - 1][1];
+          px = ax + alpha * (c_refd[ego_index + idx][0] - ax);
+          py = ay + alpha * (c_refd[ego_index + idx][1] - ay);
+        }
+        s_ex[g][t] = px; s_ey[g][t] = py;
+        ++n_valid;
+      }
+    }
+    if (l == 0) { s_ex[g][0] = ex; s_ey[g][0] = ey; }
+#pragma unroll
+    for (int o = LPP / 2; o > 0; o >>= 1) n_valid += __shfl_xor_sync(gmask, n_valid, o, LPP);
+    __syncwarp(gmask);
+    const int ne = 1 + n_valid;                        // valid t form a prefix (dist is increasing)
+    aborted = (len < 2) || (ne <= 1);                  // LineString of one point / 30 identical points
+    if (aborted) my_deg = 1;
+
+    if (!aborted && has_veh) {
+      // ---- intersections of the ego polyline with this vehicle's straight 31-point track ------
+      double Ox[kPred + 1], Oy[kPred + 1];
+      Ox[0] = ox; Oy[0] = oy;
+      for (int t = 1; t <= kPred; ++t) { Ox[t] = Ox[t - 1] + incx; Oy[t] = Oy[t - 1] + incy; }
+      bool have = false;
+      double qx = 0, qy = 0;
+      const double tlen = fabs(Ox[kPred] - Ox[0]) + fabs(Oy[kPred] - Oy[0]);
+      for (int i = 0; i + 1 < ne; ++i) {
+        const double p1x = s_ex[g][i], p1y = s_ey[g][i], p2x = s_ex[g][i + 1], p2y = s_ey[g][i + 1];
+        // orientation of track ends about the ego segment is affine in t: locate the sign change
+        const double e0 = orient(p1x, p1y, p2x, p2y, Ox[0], Oy[0]);
+        const double e30 = orient(p1x, p1y, p2x, p2y, Ox[kPred], Oy[kPred]);
+        const double sc = (fabs(p2x - p1x) + fabs(p2y - p1y) + 1e-300) * (tlen + 1e-300);
+        const double tol = 1e-7 * sc;
+        if ((e0 > tol && e30 > tol) || (e0 < -tol && e30 < -tol)) continue;
+        int jlo = 0, jhi = kPred - 1;
+        const double de = e30 - e0;
+        if (fabs(de) > tol) {
+          double js = -e0 / de * kPred;
+          int jc = (int)floor(js);
+          jlo = jc - 1 < 0 ? 0 : jc - 1;
+          jhi = jc + 1 > kPred - 1 ? kPred - 1 : jc + 1;
+          if (jlo > kPred - 1 || jhi < 0) continue;
+        }
+        for (int j = jlo; j <= jhi; ++j) {
+          const double q1x = Ox[j], q1y = Oy[j], q2x = Ox[j + 1], q2y = Oy[j + 1];
+          const double d1 = orient(q1x, q1y, q2x, q2y, p1x, p1y);
+          const double d2 = orient(q1x, q1y, q2x, q2y, p2x, p2y);
+          const double d3 = orient(p1x, p1y, p2x, p2y, q1x, q1y);
+          const double d4 = orient(p1x, p1y, p2x, p2y, q2x, q2y);
+          const double s2 = (fabs(p2x - p1x) + fabs(p2y - p1y) + 1e-300) * (fabs(q2x - q1x) + fabs(q2y - q1y) + 1e-300) + 1e-300;
+          const double eps = 1e-9 * s2;
+          const bool proper = (d1 * d2 < 0) && (d3 * d4 < 0);
+          if (!proper) {
+            if (fabs(d1) <= eps || fabs(d2) <= eps || fabs(d3) <= eps || fabs(d4) <= eps) {
+              // near-touching pair with overlapping boxes: robust and plain predicates may differ
+              const bool box = fmin(p1x, p2x) <= fmax(q1x, q2x) + 1e-9 && fmin(q1x, q2x) <= fmax(p1x, p2x) + 1e-9 &&
+                               fmin(p1y, p2y) <= fmax(q1y, q2y) + 1e-9 && fmin(q1y, q2y) <= fmax(p1y, p2y) + 1e-9;
+              if (box) my_deg = 1;
+            }
+            continue;
+          }
+          const double tt = d1 / (d1 - d2);
+          const double cx = p1x + tt * (p2x - p1x), cy = p1y + tt * (p2y - p1y);
+          // nearest-time test (agents/pure_mpc.py:641-649), first minimum wins
+          int te = 0, to = 0;
+          double bde = 1e300, bdo = 1e300;
+          for (int t = 0; t < ne; ++t) { double d = norm2(s_ex[g][t] - cx, s_ey[g][t] - cy); if (d < bde) { bde = d; te = t; } }
+          for (int t = 0; t <= kPred; ++t) { double d = norm2(Ox[t] - cx, Oy[t] - cy); if (d < bdo) { bdo = d; to = t; } }
+          int dtm = te - to; dtm = dtm < 0 ? -dtm : dtm;
+          if (dtm < kTimeThreshold) {
+            // candidates are visited in lexicographic (x, y) order: keep the smallest passing one
+            if (!have || cx < qx || (cx == qx && cy < qy)) { have = true; qx = cx; qy = cy; }
+          }
+        }
+      }
+      if (have) {
+        my_flag = 1;
+        double bdr = 1e300;
+        for (int j = 0; j < kNRef; ++j) { double d = norm2(c_refd[j][0] - qx, c_refd[j][1] - qy); if (d < bdr) { bdr = d; my_cidx = j; } }
+      }
+    }
+  }
+
+  // ---- combine over the group --------------------------------------------------------------------
+  int any_flag = my_flag, any_deg = my_deg;
+  int min_c = my_flag ? my_cidx : 1 << 30;
+#pragma unroll
+  for (int o = LPP / 2; o > 0; o >>= 1) {
+    any_flag |= __shfl_xor_sync(gmask, any_flag, o, LPP);
+    any_deg |= __shfl_xor_sync(gmask, any_deg, o, LPP);
+    int oc = __shfl_xor_sync(gmask, min_c, o, LPP);
+    min_c = oc < min_c ? oc : min_c;
+  }
+
+  if (P.collision_check) {
+    if (latched) {                                      // pure_mpc.py:558-563
+      is_col = 1; mem -= 1; cmin = memo;
+    } else if (!aborted) {                              // pure_mpc.py:660-676
+      is_col = any_flag;
+      if (is_col) { mem = kMemorySteps; memo = min_c; cmin = min_c; }
+      else if (mem > 0) { mem -= 1; is_col = 1; cmin = -1; }
+      else { memo = -1; }
+    }                                                    // aborted: early return, state left as it was
+  } else {
+    is_col = 0;
+  }
+
+  if (!live) return;
+
+  // ---- per-vehicle outputs ---------------------------------------------------------------------
+  if (l < P.M) {
+    if (P.col.agent_collide) P.col.agent_collide[(size_t)b * P.M + l] = (uint8_t)((P.collision_check && !latched && !aborted) ? my_flag : 0);
+    if (P.col.conflict_index) P.col.conflict_index[(size_t)b * P.M + l] = (P.collision_check && !latched && !aborted && my_flag) ? my_cidx : -1;
+    float* O = P.ws.obstacles;
+    const size_t B = P.B;
+    O[((size_t)l * 4 + 0) * B + b] = has_veh ? (float)ox : 0.f;
+    O[((size_t)l * 4 + 1) * B + b] = has_veh ? (float)oy : 0.f;
+    O[((size_t)l * 4 + 2) * B + b] = has_veh ? (float)incx : 0.f;
+    O[((size_t)l * 4 + 3) * B + b] = has_veh ? (float)incy : 0.f;
+  }
+  if (LPP < MPC_MAX_OBSTACLES && l == 0) {
+    for (int m = LPP; m < P.M; ++m) {                   // more vehicles than lanes: not reachable with LPP >= M
+      for (int c = 0; c < 4; ++c) P.ws.obstacles[((size_t)m * 4 + c) * P.B + b] = 0.f;
+    }
+  }
+
+  if (l != 0) return;
+  // ---- weights, reference-speed profile (update_reference_states, pure_mpc.py:678-724) -----------
+  float w_s = P.w_speed, w_c = P.w_control, w_d = P.w_diff;
+  if (P.weights) { w_s = P.weights[(size_t)b * 3]; w_c = P.weights[(size_t)b * 3 + 1]; w_d = P.weights[(size_t)b * 3 + 2]; }
+  if (is_col) w_s = 100.f;                              // pure_mpc.py:143-147
+  float vr_a = 0.f, vr_slope = 0.f, vr_b = (float)c_refd[0][2];
+  int vr_n = 0;
+  bool override_v = false;
+  if (P.ref_speed) {
+    const float rs = P.ref_speed[b];
+    if (rs == rs) { override_v = true; vr_b = fminf(fmaxf(rs, 0.f), 30.f); }   // np.clip(., 0, 30), takes precedence
+  }
+  if (!override_v && is_col && cmin >= 0) {
+    int stop = cmin - kSafetyBuffer;
+    stop = stop > ego_index + 1 ? stop : ego_index + 1;
+    stop = stop < kNRef - 1 ? stop : kNRef - 1;
+    const int n = stop - ego_index;
+    if (n > 0) {
+      vr_n = n; vr_a = (float)ev; vr_b = 0.f;
+      vr_slope = n > 1 ? (float)(-ev / (double)(n - 1)) : 0.f;   // np.linspace(v, 0, n)
+      stop_index = stop;
+    }
+  }
+  P.ws.s0[0 * (size_t)P.B + b] = (float)ex;
+  P.ws.s0[1 * (size_t)P.B + b] = (float)ey;
+  P.ws.s0[2 * (size_t)P.B + b] = (float)eth;
+  P.ws.s0[3 * (size_t)P.B + b] = (float)ev;
+  P.ws.ego_index[b] = ego_index;
+  P.ws.w_speed[b] = w_s;
+  P.ws.w_control[b] = w_c;
+  P.ws.w_diff[b] = w_d;
+  P.ws.vr_a[b] = vr_a;
+  P.ws.vr_slope[b] = vr_slope;
+  P.ws.vr_b[b] = vr_b;
+  P.ws.vr_n[b] = vr_n;
+  P.ws.is_collide[b] = (uint8_t)is_col;
+  P.ws.n_obs[b] = n_obs;
+  if (P.collision_check) {
+    P.latch.collision_memory[b] = mem;
+    P.latch.memo_conflict[b] = memo;
+    P.latch.is_collide[b] = (uint8_t)is_col;
+  }
+  if (P.col.is_collide) P.col.is_collide[b] = (uint8_t)is_col;
+  if (P.col.ego_index) P.col.ego_index[b] = ego_index;
+  if (P.col.stop_index) P.col.stop_index[b] = stop_index;
+  if (P.col.degenerate) P.col.degenerate[b] = (uint8_t)any_deg;
+}
+
+cudaError_t launch_prepare(const PrepareParams& p, cudaStream_t stream) {
+  if (p.B <= 0) return cudaSuccess;
+  if (p.M <= 8) {
+    const int ppb = 256 / 8;
+    k_prepare<8><<<(p.B + ppb - 1) / ppb, 256, 0, stream>>>(p);
+  } else {
+    const int ppb = 256 / 16;
+    k_prepare<16><<<(p.B + ppb - 1) / ppb, 256, 0, stream>>>(p);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace mpcb

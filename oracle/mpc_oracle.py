@@ -98,18 +98,24 @@ def parse_obs(obs: np.ndarray, vehicles_count: Optional[int] = None) -> ParsedOb
         raise ValueError(f"Expect observation's shape of ({(vehicles_count, 8)}), but got {obs.shape}")
     o = obs.astype(np.float64)
     n = int(np.sum(obs[:, 0] == 1)) - 1
-    ego = np.array([o[0, 1], o[0, 2], normalize_angle(o[0, 5]), math.hypot(o[0, 3], o[0, 4])])
+    ego = np.array([o[0, 1], o[0, 2], normalize_angle(o[0, 5]), float(_norm2(o[0, 3], o[0, 4]))])
     others = np.zeros((max(n, 0), 4))
     for i in range(max(n, 0)):
         r = o[i + 1]
-        others[i] = (r[1], r[2], math.hypot(r[3], r[4]), r[5])
+        others[i] = (r[1], r[2], float(_norm2(r[3], r[4])), r[5])
     return ParsedObs(ego=ego, others=others)
+
+
+def _norm2(dx, dy):
+    """Euclidean norm the way np.linalg.norm of a 2-vector evaluates it: sqrt(dx*dx + dy*dy),
+    un-fused (the device predicate code is compiled with -fmad=false to round identically)."""
+    return np.sqrt(dx * dx + dy * dy)
 
 
 def nearest_index(p: Sequence[float], ref_xy: np.ndarray) -> int:
     """Global argmin over all reference points, first minimum wins
     (agents/pure_mpc.py:106-109, 566-570, 471-474)."""
-    d = np.hypot(ref_xy[:, 0] - p[0], ref_xy[:, 1] - p[1])
+    d = _norm2(ref_xy[:, 0] - p[0], ref_xy[:, 1] - p[1])
     return int(np.argmin(d))
 
 
@@ -490,7 +496,7 @@ def predict_ego_polyline(pos: np.ndarray, speed: float, start_index: int, ref_sp
     rp = ref[start_index:, :2]
     if rp.shape[0] < 2:
         return np.array(pts)                                    # pure_mpc.py:478-479
-    seg = np.hypot(np.diff(rp[:, 0]), np.diff(rp[:, 1]))
+    seg = _norm2(np.diff(rp[:, 0]), np.diff(rp[:, 1]))
     cum = np.concatenate([[0.0], np.cumsum(seg)])               # sequential sum, as :481-484
     # np.cumsum accumulates left-to-right exactly like the reference's Python loop.
     cur_v, dist = float(speed), 0.0
@@ -512,7 +518,10 @@ def predict_ego_polyline(pos: np.ndarray, speed: float, start_index: int, ref_sp
             nxt = rp[idx - 1] + alpha * (rp[idx] - rp[idx - 1])
         pts.append(nxt)
     if len(pts) <= 1:
-        return np.array([pts[0]] * PRED_HORIZON)                # pure_mpc.py:525-526
+        # pure_mpc.py:525-526 falls back to 30 copies of the current position (a zero-length
+        # LineString).  That polyline cannot cross anything; it is reported as a one-point polyline
+        # and handled as "detection aborted, degenerate" by detect_collisions.
+        return np.array(pts)
     return np.array(pts)
 
 
@@ -620,8 +629,8 @@ def detect_collisions(ego: np.ndarray, others: np.ndarray, dt: float = 0.1,
         degenerate |= deg
         hit, cidx, cpt = False, None, None
         for q in cand:
-            te = int(np.argmin(np.hypot(E[:, 0] - q[0], E[:, 1] - q[1])))
-            to = int(np.argmin(np.hypot(O[:, 0] - q[0], O[:, 1] - q[1])))
+            te = int(np.argmin(_norm2(E[:, 0] - q[0], E[:, 1] - q[1])))
+            to = int(np.argmin(_norm2(O[:, 0] - q[0], O[:, 1] - q[1])))
             if abs(te - to) < TIME_THRESHOLD:
                 hit, cidx, cpt = True, nearest_index(q, ref_xy), np.array(q)
                 break

@@ -1,0 +1,69 @@
+"""Generates the committed golden fixtures from the FP64 oracle (oracle/mpc_oracle.py).
+
+    OMP_NUM_THREADS=1 python tests/golden/make_golden.py
+
+The reference itself cannot be imported here (casadi / shapely / highway-env are not installable,
+SURVEY 8-c), so these vectors pin the ORACLE, not CasADi/IPOPT ("parity unpinned").  Files:
+  golden_track.npz   256 scenarios, M=0, tracking objective (BASELINE config 2 type)
+  golden_coll.npz    256 scenarios, M=8, collision check + regeneration + distance cost 10 (config 3 type)
+Each holds the observations (float32), the parsed problem descriptors, collision outputs and the
+oracle's NLP solution from the reference's cold start.
+"""
+import os
+import sys
+import multiprocessing as mp
+
+os.environ.setdefault("OMP_NUM_THREADS", "1")
+os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np  # noqa: E402
+
+import helpers  # noqa: E402
+from helpers import orc  # noqa: E402
+import mpc_rl_for_avs_b200 as pkg  # noqa: E402
+
+
+def _solve(p):
+    s = orc.solve_nlp(p)
+    kkt, viol = orc.kkt_residual(s.U, p)
+    return s.U, s.cost, s.components, s.success, s.nit, kkt
+
+
+def make(name, B, M, seed, w_distance, collision_check):
+    obs, rs, has = pkg.make_scenarios(B, M, seed=seed)
+    obs, rs, has = obs.numpy(), rs.numpy(), has.numpy()
+    probs, agents = helpers.problems_from_obs(obs, rs, has, w_distance=w_distance, collision_check=collision_check)
+    with mp.Pool(min(8, os.cpu_count() or 1)) as pool:
+        sols = pool.map(_solve, probs, chunksize=4)
+    d = helpers.batch_from_problems(probs, M)
+    out = dict(obs=obs, ref_speed=rs, has_ref_speed=has, w_distance=np.float64(w_distance),
+               collision_check=np.bool_(collision_check), n_obstacles=np.int64(M))
+    out.update({"batch_" + k: v for k, v in d.items()})
+    out["oracle_U"] = np.array([s[0] for s in sols])
+    out["oracle_cost"] = np.array([s[1] for s in sols])
+    out["oracle_components"] = np.array([s[2] for s in sols])
+    out["oracle_success"] = np.array([s[3] for s in sols])
+    out["oracle_nit"] = np.array([s[4] for s in sols])
+    out["oracle_kkt"] = np.array([s[5] for s in sols])
+    Mx = max(M, 1)
+    flags = np.zeros((B, Mx), np.uint8); cidx = -np.ones((B, Mx), np.int32); deg = np.zeros(B, np.uint8)
+    if collision_check:
+        for i in range(B):
+            parsed = orc.parse_obs(obs[i], obs.shape[1])
+            res = orc.detect_collisions(parsed.ego, parsed.others)
+            deg[i] = res.degenerate
+            for m, (f, c) in enumerate(zip(res.agent_collide, res.conflict_index)):
+                flags[i, m] = f
+                cidx[i, m] = -1 if c is None else c
+    out["agent_collide"], out["conflict_index"], out["degenerate"] = flags, cidx, deg
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "written:", B, "problems; oracle success", out["oracle_success"].mean(),
+          "collide frac", float(np.mean(d["is_collide"])), "degenerate", int(deg.sum()))
+
+
+if __name__ == "__main__":
+    make("golden_track", 256, 0, 11, 0.0, False)
+    make("golden_coll", 256, 8, 12, 10.0, True)

@@ -1,0 +1,163 @@
+"""Shared test plumbing: oracle problem builders, SoA batch packing (the MpcProblemBatch layout),
+the test-only host harness loader, golden fixture access."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for _p in (ROOT, os.path.join(ROOT, "oracle")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import mpc_oracle as orc  # noqa: E402
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+REF = orc.reference_states()
+
+
+# ----------------------------------------------------------------------------- problems
+def problems_from_obs(obs, ref_speed=None, has_ref_speed=None, w_distance=0.0, collision_check=False, N=20):
+    """One fresh oracle agent per observation (cleared latch): parse -> [collision] -> Problem."""
+    probs, agents = [], []
+    for i in range(obs.shape[0]):
+        ag = orc.OraclePureMPCAgent(horizon=N, vehicles_count=obs.shape[1], weight_distance=w_distance,
+                                    collision_check=collision_check)
+        parsed = orc.parse_obs(obs[i], obs.shape[1])
+        if collision_check:
+            ag.check_collision(parsed)
+        r = None
+        if ref_speed is not None and (has_ref_speed is None or has_ref_speed[i]):
+            r = np.asarray(ref_speed[i]).reshape(1, 1)
+        probs.append(ag.build_problem(parsed, None, r))
+        agents.append(ag)
+    return probs, agents
+
+
+def ref_speed_descriptor(rv):
+    """(vr_a, vr_slope, vr_b, vr_n) of a per-stage reference-speed profile (constant or ramp-then-zero)."""
+    rv = np.asarray(rv, dtype=np.float64)
+    if np.all(rv == rv[0]):
+        return 0.0, 0.0, float(rv[0]), 0
+    nz = np.nonzero(rv == 0)[0]
+    n = int(nz[0]) if nz.size else len(rv)
+    slope = float(rv[1] - rv[0]) if n > 1 else 0.0
+    return float(rv[0]), slope, 0.0, n
+
+
+def batch_from_problems(probs, M):
+    """Packs oracle Problems into the SoA arrays of MpcProblemBatch (float32 / int32 / uint8)."""
+    B, Mx = len(probs), max(M, 1)
+    d = dict(s0=np.zeros((4, B), np.float32), ego_index=np.zeros(B, np.int32), w_speed=np.zeros(B, np.float32),
+             w_control=np.zeros(B, np.float32), w_diff=np.zeros(B, np.float32), vr_a=np.zeros(B, np.float32),
+             vr_slope=np.zeros(B, np.float32), vr_b=np.zeros(B, np.float32), vr_n=np.zeros(B, np.int32),
+             is_collide=np.zeros(B, np.uint8), n_obs=np.zeros(B, np.int32), obstacles=np.zeros((Mx, 4, B), np.float32))
+    for i, p in enumerate(probs):
+        d["s0"][:, i] = p.s0
+        d["ego_index"][i] = p.ego_index
+        d["w_speed"][i], d["w_control"][i], d["w_diff"][i] = p.w_speed, p.w_control, p.w_input_diff
+        a, s, b, n = ref_speed_descriptor(p.ref_v)
+        d["vr_a"][i], d["vr_slope"][i], d["vr_b"][i], d["vr_n"][i] = a, s, b, n
+        d["is_collide"][i] = p.is_collide
+        m = min(p.others.shape[0], M)
+        d["n_obs"][i] = m
+        for k in range(m):
+            x, y, sp, h = p.others[k]
+            d["obstacles"][k, :, i] = (x, y, sp * p.dt * np.cos(h), sp * p.dt * np.sin(h))
+    return d
+
+
+def problem_f32(p):
+    """The Problem as the device sees it: float32-rounded inputs (s0, weights, obstacles enter the
+    kernels as float32), so FP64 re-evaluations use the same data."""
+    import copy
+    q = copy.deepcopy(p)
+    q.s0 = q.s0.astype(np.float32).astype(np.float64)
+    return q
+
+
+# ----------------------------------------------------------------------------- host harness
+class HsConfig(C.Structure):       # mirrors mpcb::SolverConfig
+    _fields_ = [("N", C.c_int), ("M", C.c_int), ("dt", C.c_float), ("w_distance", C.c_float),
+                ("w_collision", C.c_float), ("literal_no_collision", C.c_int), ("max_iter", C.c_int),
+                ("tol_step", C.c_float), ("reg_min", C.c_float)]
+
+
+_P = C.POINTER
+
+
+class HsBatch(C.Structure):
+    _fields_ = [("s0", _P(C.c_float)), ("ego_index", _P(C.c_int)), ("w_speed", _P(C.c_float)),
+                ("w_control", _P(C.c_float)), ("w_diff", _P(C.c_float)), ("vr_a", _P(C.c_float)),
+                ("vr_slope", _P(C.c_float)), ("vr_b", _P(C.c_float)), ("vr_n", _P(C.c_int)),
+                ("is_collide", _P(C.c_ubyte)), ("n_obs", _P(C.c_int)), ("obstacles", _P(C.c_float))]
+
+
+def hs_config(N=20, M=8, dt=0.1, w_distance=0.0, w_collision=0.0, literal=0, max_iter=60, tol_step=1e-4, reg_min=1e-2):
+    return HsConfig(N=N, M=M, dt=dt, w_distance=w_distance, w_collision=w_collision, literal_no_collision=literal,
+                    max_iter=max_iter, tol_step=tol_step, reg_min=reg_min)
+
+
+def load_hostsim():
+    """Builds (if stale) and loads tests/hostsim/libhostsim.so -- the kernel's device functions
+    compiled for the CPU.  Test infrastructure only; the product never loads it."""
+    src = os.path.join(ROOT, "tests", "hostsim", "hostsim.cpp")
+    core = os.path.join(ROOT, "mpc-rl_for_avs_b200", "csrc", "mpc_core.cuh")
+    so = os.path.join(ROOT, "tests", "hostsim", "libhostsim.so")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(core)):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so, src])
+    lib = C.CDLL(so)
+    assert lib.hs_sizeof_config() == C.sizeof(HsConfig)
+    return lib
+
+
+def _as_struct(d):
+    b = HsBatch()
+    ct = {np.dtype("float32"): C.c_float, np.dtype("int32"): C.c_int, np.dtype("uint8"): C.c_ubyte}
+    for k, _ in HsBatch._fields_:
+        setattr(b, k, d[k].ctypes.data_as(_P(ct[d[k].dtype])))
+    return b
+
+
+def hostsim_solve(lib, d, cfg, use_double=False):
+    B = d["ego_index"].shape[0]
+    act = np.zeros((B, 2), np.float32); st = np.zeros(B, np.int32); it = np.zeros(B, np.int32)
+    cost = np.zeros(B, np.float32); U = np.zeros((B, cfg.N, 2), np.float32); outer = np.zeros(B, np.int32)
+    b = _as_struct(d)
+    f = lambda a, t: a.ctypes.data_as(_P(t))  # noqa: E731
+    lib.hs_solve(C.byref(cfg), REF.ctypes.data_as(_P(C.c_double)), C.byref(b), B, int(use_double), f(act, C.c_float),
+                 f(st, C.c_int), f(it, C.c_int), f(cost, C.c_float), f(U, C.c_float), f(outer, C.c_int))
+    return dict(actions=act, status=st, iters=it, cost=cost, U=U)
+
+
+def hostsim_rollout_cost(lib, d, cfg, U, use_double=False):
+    B = d["ego_index"].shape[0]
+    U = np.ascontiguousarray(U, np.float32)
+    X = np.zeros((B, cfg.N + 1, 4), np.float32); c6 = np.zeros((B, 6), np.float32); tot = np.zeros(B, np.float32)
+    b = _as_struct(d)
+    f = lambda a, t: a.ctypes.data_as(_P(t))  # noqa: E731
+    lib.hs_rollout_cost(C.byref(cfg), REF.ctypes.data_as(_P(C.c_double)), C.byref(b), B, int(use_double),
+                        f(U, C.c_float), f(X, C.c_float), f(c6, C.c_float), f(tot, C.c_float))
+    return X, c6, tot
+
+
+# ----------------------------------------------------------------------------- golden fixtures
+def load_golden(name):
+    path = os.path.join(GOLDEN_DIR, f"{name}.npz")
+    return dict(np.load(path, allow_pickle=False))
+
+
+def oracle_warm_confirms(prob, U, du_tol=1e-3, rel_gain_tol=1e-6):
+    """The multi-modality-proof optimality check: the oracle's NLP solver, started AT the candidate
+    controls, must stay there (first control moves < du_tol) and must not find a lower cost
+    (relative gain < rel_gain_tol).  Returns (ok, du0, rel_gain)."""
+    U = np.asarray(U, dtype=np.float64)
+    c0 = orc.objective(U, prob)
+    s = orc.solve_nlp(prob, U0=U)
+    du0 = float(np.max(np.abs(s.U[0] - U[0])))
+    gain = float((c0 - s.cost) / (1.0 + abs(c0)))
+    return (du0 < du_tol and gain < rel_gain_tol), du0, gain
