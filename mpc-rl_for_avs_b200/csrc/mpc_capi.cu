@@ -185,6 +185,7 @@ MPC_API int mpc_workspace_batch(MpcHandle* h, MpcProblemBatch* out) {
 
 static int check_batch(MpcHandle* h, const MpcProblemBatch* b, int B) {
   if (!h) return MPC_ERR_BAD_ARG;
+  if (B == 0) return MPC_OK;
   if (!b || B < 0) return fail(h, MPC_ERR_BAD_ARG, "null batch or negative size");
   if (!b->s0 || !b->ego_index || !b->w_speed || !b->w_control || !b->w_diff || !b->vr_a || !b->vr_slope || !b->vr_b || !b->vr_n)
     return fail(h, MPC_ERR_BAD_ARG, "MpcProblemBatch: a required array is null");
@@ -243,6 +244,7 @@ MPC_API int mpc_solve(MpcHandle* h, const MpcProblemBatch* batch, int B, const M
 MPC_API int mpc_prepare(MpcHandle* h, const float* obs, const float* ref_speed, const float* weights, const uint8_t* reset_mask,
                 const MpcLatchState* latch, int B, const MpcCollisionOut* col, void* stream) {
   if (!h) return MPC_ERR_BAD_ARG;
+  if (B == 0) return MPC_OK;
   if (!obs || B < 0) return fail(h, MPC_ERR_BAD_ARG, "mpc_prepare: obs is null or B < 0");
   if (B > h->max_batch) return fail(h, MPC_ERR_TOO_LARGE, "mpc_prepare: B exceeds max_batch of mpc_create");
   if (h->cfg.collision_check && (!latch || !latch->collision_memory || !latch->memo_conflict || !latch->is_collide))
@@ -281,6 +283,7 @@ MPC_API int mpc_predict_host(MpcHandle* h, const float* obs_host, const float* r
                      const uint8_t* reset_mask_host, int B, float* actions_host, int32_t* status_host,
                      uint8_t* is_collide_host, int64_t* h2d_bytes, int64_t* d2h_bytes) {
   if (!h) return MPC_ERR_BAD_ARG;
+  if (B == 0) return MPC_OK;
   if (!obs_host || !actions_host || B < 0) return fail(h, MPC_ERR_BAD_ARG, "mpc_predict_host: null obs/actions or B < 0");
   if (B > h->max_batch) return fail(h, MPC_ERR_TOO_LARGE, "mpc_predict_host: B exceeds max_batch of mpc_create");
   if (B == 0) return MPC_OK;

@@ -34,7 +34,7 @@
 namespace mpcb {
 
 constexpr int kNRef = 85;          // agents/base_agent.py:127-152 (40 + 20 + 25 rows)
-constexpr int kRefStride = 5;      // x, y, heading, sin h, cos h
+constexpr int kRefStride = 3;      // heading, sin h, cos h (float table); x, y live in an FP64 table
 constexpr int kMaxObstacles = 16;
 
 template <typename T> struct Lim {
@@ -85,6 +85,10 @@ struct SolverConfig {
 
 // ---- per-problem scalars -------------------------------------------------------------
 template <typename T> struct ProblemScalars {
+  // Positions are carried RELATIVE to the ego's initial position (x0, y0): the rollout then starts
+  // at 0 and stays within ~25 m, and path / obstacle offsets are formed in FP64 before rounding,
+  // so FP32 tracking and distance residuals keep ~1e-7 m accuracy instead of ulp(50 m).
+  double x0, y0;
   int ego_index;          // nearest reference row (pure_mpc.py:106-109)
   int n_obs;              // present obstacles (<= M)
   int is_collide;
@@ -96,6 +100,22 @@ template <typename T> struct ProblemScalars {
   T vr_a, vr_slope, vr_b;
   int vr_n;
 };
+
+// reference path: FP64 positions (85 x 2) and a scalar-typed (heading, sin h, cos h) table
+template <typename T> struct RefTab {
+  const T* hsc;
+  const double* xy;
+};
+template <typename T> struct RefPoint { T x, y, h, sh, ch; };
+template <typename T> MPC_HD RefPoint<T> ref_point(const RefTab<T>& rt, const ProblemScalars<T>& p, int k) {
+  int j = p.ego_index + k;                              // j(k) = min(ego_index + k, 84), pure_mpc.py:129
+  j = j < kNRef - 1 ? j : kNRef - 1;
+  RefPoint<T> r;
+  r.x = T(rt.xy[2 * j] - p.x0);
+  r.y = T(rt.xy[2 * j + 1] - p.y0);
+  r.h = rt.hsc[j * kRefStride]; r.sh = rt.hsc[j * kRefStride + 1]; r.ch = rt.hsc[j * kRefStride + 2];
+  return r;
+}
 
 template <typename T> MPC_HD T ref_speed_at(const ProblemScalars<T>& p, int k) {
   return (k < p.vr_n) ? p.vr_a + T(k) * p.vr_slope : p.vr_b;
@@ -160,16 +180,14 @@ MPC_HD void euler_step(T& x, T& y, T& th, T& v, T a, const Steer<T>& st, T dt, T
 // comp[0..5] accumulate the reference's six un-weighted components (pure_mpc.py:215-216);
 // returns the weighted stage objective (pure_mpc.py:204-212 + archive terms).
 template <typename T>
-MPC_HD T stage_cost(const SolverConfig& cfg, const ProblemScalars<T>& p, const T* __restrict__ ref,
+MPC_HD T stage_cost(const SolverConfig& cfg, const ProblemScalars<T>& p, const RefTab<T>& ref,
                     const Slots<T>& sl, int k, T x, T y, T th, T v, T a, T d, T ap, T dp, T* comp) {
-  int j = p.ego_index + k;
-  j = j < kNRef - 1 ? j : kNRef - 1;
-  const T* r = ref + j * kRefStride;
-  T dx = x - r[0], dy = y - r[1];
-  T perp = dx * r[3] - dy * r[4];
-  T para = dx * r[4] + dy * r[3];
+  const RefPoint<T> r = ref_point(ref, p, k);
+  T dx = x - r.x, dy = y - r.y;
+  T perp = dx * r.sh - dy * r.ch;
+  T para = dx * r.ch + dy * r.sh;
   T dv = v - ref_speed_at(p, k);
-  T dth = th - r[2];
+  T dth = th - r.h;
   T st = T(4) * perp * perp + T(2) * para * para + p.w_speed * dv * dv + T(0.5) * dth * dth;
   T ct = T(0.01) * (a * a + d * d);
   T df = T(0);
@@ -233,7 +251,7 @@ template <typename T> MPC_HD Box<T> control_box(T th, T v, T dt) {
 // Controls are used as stored (no clamping): this is also the parity entry point for
 // "rollout + six cost components" (mpc_rollout_cost).
 template <typename T>
-MPC_HD T rollout_nominal(const SolverConfig& cfg, const ProblemScalars<T>& p, const T* __restrict__ ref,
+MPC_HD T rollout_nominal(const SolverConfig& cfg, const ProblemScalars<T>& p, const RefTab<T>& ref,
                          const Slots<T>& sl, T* comp /*6 or null*/) {
   const int N = cfg.N;
   T x = sl.X(0, 0), y = sl.X(0, 1), th = sl.X(0, 2), v = sl.X(0, 3);
@@ -247,6 +265,20 @@ MPC_HD T rollout_nominal(const SolverConfig& cfg, const ProblemScalars<T>& p, co
     ap = a; dp = d;
   }
   return J;
+}
+
+// final_state component of the reference's cost_fn (agents/pure_mpc.py:195-202; note the
+// (y + y_ref) sign) -- reported, never optimised.  Needs absolute y: formed in FP64.
+template <typename T>
+MPC_HD T final_state_component(const SolverConfig& cfg, const ProblemScalars<T>& p, const RefTab<T>& ref, const Slots<T>& sl) {
+  const int N = cfg.N;
+  const RefPoint<T> r = ref_point(ref, p, N);
+  int j = p.ego_index + N;
+  j = j < kNRef - 1 ? j : kNRef - 1;
+  T ex = sl.X(N, 0) - r.x;
+  T ey = T((p.y0 + double(sl.X(N, 1))) + ref.xy[2 * j + 1]);
+  T ev = sl.X(N, 3) - ref_speed_at(p, N), eth = sl.X(N, 2) - r.h;
+  return T(100) * (ex * ex + ey * ey + T(20) * ev * ev + eth * eth);
 }
 
 // ---- 2x2 box QP --------------------------------------------------------------------------
@@ -289,7 +321,7 @@ MPC_HD constexpr int sym6(int i, int j) { return i <= j ? (i * (13 - i)) / 2 + (
 // Fills K (2x6 per stage) and F (feed-forward) from the nominal (X, U); returns the two
 // coefficients of the predicted objective change  dJ(alpha) = alpha*d1 + alpha^2*d2.
 template <typename T>
-MPC_HD void backward_pass(const SolverConfig& cfg, const ProblemScalars<T>& p, const T* __restrict__ ref,
+MPC_HD void backward_pass(const SolverConfig& cfg, const ProblemScalars<T>& p, const RefTab<T>& ref,
                           const Slots<T>& sl, T mu, T hs, T* d1_out, T* d2_out) {
   // hs in [0,1] scales the second-order dynamics terms and the negative (tangential) obstacle
   // curvature: 0 = Gauss-Newton/iLQR model (robust far from the solution), 1 = exact Hessian.
@@ -320,15 +352,13 @@ MPC_HD void backward_pass(const SolverConfig& cfg, const ProblemScalars<T>& p, c
     T lx = T(0), ly = T(0), lth = T(0), lv = T(0);
     T lxx = T(0), lxy = T(0), lyy = T(0), lthth = T(0), lvv = T(0);
     if (!cfg.literal_no_collision) {
-      int j = p.ego_index + k;
-      j = j < kNRef - 1 ? j : kNRef - 1;
-      const T* r = ref + j * kRefStride;
-      const T sh = r[3], ch = r[4];
-      T dx = x - r[0], dy = y - r[1];
+      const RefPoint<T> r = ref_point(ref, p, k);
+      const T sh = r.sh, ch = r.ch;
+      T dx = x - r.x, dy = y - r.y;
       T perp = dx * sh - dy * ch, para = dx * ch + dy * sh;
       lx = T(80) * perp * sh + T(40) * para * ch;
       ly = -T(80) * perp * ch + T(40) * para * sh;
-      lth = T(10) * (th - r[2]);
+      lth = T(10) * (th - r.h);
       T wv = T(20) * p.w_speed;
       lv = wv * (v - ref_speed_at(p, k));
       lxx = T(80) * sh * sh + T(40) * ch * ch;
@@ -549,7 +579,7 @@ MPC_HD void backward_pass(const SolverConfig& cfg, const ProblemScalars<T>& p, c
 // kCommit=true : overwrite (X, U) in place with the new trajectory.  Returns the objective;
 // *maxdu = max |u_new - u_old| over the horizon.
 template <typename T, bool kCommit>
-MPC_HD T forward_pass(const SolverConfig& cfg, const ProblemScalars<T>& p, const T* __restrict__ ref,
+MPC_HD T forward_pass(const SolverConfig& cfg, const ProblemScalars<T>& p, const RefTab<T>& ref,
                       const Slots<T>& sl, T alpha, T* maxdu) {
   const int N = cfg.N;
   const T dt = T(cfg.dt);
@@ -598,7 +628,7 @@ template <typename T> struct SolveState {
 };
 
 template <typename T>
-MPC_HD void solve_begin(const SolverConfig& cfg, const ProblemScalars<T>& p, const T* __restrict__ ref,
+MPC_HD void solve_begin(const SolverConfig& cfg, const ProblemScalars<T>& p, const RefTab<T>& ref,
                         const Slots<T>& sl, SolveState<T>& s) {
   for (int k = 0; k < cfg.N; ++k) { sl.U(k, 0) = T(0); sl.U(k, 1) = T(0); }   // cold start (pure_mpc.py:244)
   s.mu = T(0); s.hs = T(1);
@@ -643,7 +673,7 @@ MPC_HD void after_line_search(const SolverConfig& cfg, SolveState<T>& s, bool ac
 // straight-line single-problem driver (host harness; the kernel runs the same sub-steps with
 // a warp-synchronous line search, see mpc_kernels.cu)
 template <typename T>
-MPC_HD void solve_one(const SolverConfig& cfg, const ProblemScalars<T>& p, const T* __restrict__ ref,
+MPC_HD void solve_one(const SolverConfig& cfg, const ProblemScalars<T>& p, const RefTab<T>& ref,
                       const Slots<T>& sl, SolveState<T>& s) {
   solve_begin(cfg, p, ref, sl, s);
   while (!s.done) {

@@ -20,22 +20,37 @@
 
 namespace mpcb {
 
-__constant__ float c_ref[kNRef * kRefStride];
+__constant__ float c_hsc[kNRef * kRefStride];     // heading, sin h, cos h
+__constant__ double c_xy[kNRef * 2];               // path positions, FP64
 
 cudaError_t upload_ref_table_solve() {
   float h[kNRef * kRefStride];
+  double xy[kNRef * 2];
   for (int j = 0; j < kNRef; ++j) {
-    h[j * 5 + 0] = (float)kRefPath[j][0];
-    h[j * 5 + 1] = (float)kRefPath[j][1];
-    h[j * 5 + 2] = (float)kRefPath[j][3];
-    h[j * 5 + 3] = (float)sin(kRefPath[j][3]);
-    h[j * 5 + 4] = (float)cos(kRefPath[j][3]);
+    xy[2 * j] = kRefPath[j][0];
+    xy[2 * j + 1] = kRefPath[j][1];
+    h[j * kRefStride + 0] = (float)kRefPath[j][3];
+    h[j * kRefStride + 1] = (float)sin(kRefPath[j][3]);
+    h[j * kRefStride + 2] = (float)cos(kRefPath[j][3]);
   }
-  return cudaMemcpyToSymbol(c_ref, h, sizeof(h));
+  cudaError_t e = cudaMemcpyToSymbol(c_hsc, h, sizeof(h));
+  if (e != cudaSuccess) return e;
+  return cudaMemcpyToSymbol(c_xy, xy, sizeof(xy));
 }
 
+constexpr int kTabFloats = kNRef * 2 * 2 + kNRef * kRefStride + 1;   // FP64 xy (as 2 floats each) + hsc, padded to even
 size_t solve_smem_bytes(int N, int M, int tpb) {
-  return (size_t)(kNRef * kRefStride + slots_per_problem(N, M) * tpb) * sizeof(float);
+  return (size_t)(kTabFloats + slots_per_problem(N, M) * tpb) * sizeof(float);
+}
+
+// block-shared copy of the path tables at the head of dynamic shared memory
+__device__ __forceinline__ RefTab<float> stage_tables(float* smem) {
+  double* xy = reinterpret_cast<double*>(smem);
+  float* hsc = smem + kNRef * 2 * 2;
+  for (int i = threadIdx.x; i < kNRef * 2; i += blockDim.x) xy[i] = c_xy[i];
+  for (int i = threadIdx.x; i < kNRef * kRefStride; i += blockDim.x) hsc[i] = c_hsc[i];
+  __syncthreads();
+  return RefTab<float>{hsc, xy};
 }
 
 __device__ __forceinline__ void load_problem(const MpcProblemBatch& b, int B, int i, const SolverConfig& cfg,
@@ -51,20 +66,28 @@ __device__ __forceinline__ void load_problem(const MpcProblemBatch& b, int B, in
   p.vr_slope = b.vr_slope[i];
   p.vr_b = b.vr_b[i];
   p.vr_n = b.vr_n[i];
-#pragma unroll
-  for (int c = 0; c < 4; ++c) sl.X(0, c) = b.s0[(size_t)c * B + i];
-  for (int m = 0; m < cfg.M; ++m)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) sl.O(m, c) = b.obstacles ? b.obstacles[((size_t)m * 4 + c) * B + i] : 0.f;
+  p.x0 = (double)b.s0[i];
+  p.y0 = (double)b.s0[(size_t)B + i];
+  sl.X(0, 0) = 0.f; sl.X(0, 1) = 0.f;                       // positions are relative to the ego start
+  sl.X(0, 2) = b.s0[(size_t)2 * B + i];
+  sl.X(0, 3) = b.s0[(size_t)3 * B + i];
+  for (int m = 0; m < cfg.M; ++m) {
+    if (b.obstacles) {
+      sl.O(m, 0) = (float)((double)b.obstacles[((size_t)m * 4 + 0) * B + i] - p.x0);
+      sl.O(m, 1) = (float)((double)b.obstacles[((size_t)m * 4 + 1) * B + i] - p.y0);
+      sl.O(m, 2) = b.obstacles[((size_t)m * 4 + 2) * B + i];
+      sl.O(m, 3) = b.obstacles[((size_t)m * 4 + 3) * B + i];
+    } else {
+      sl.O(m, 0) = 0.f; sl.O(m, 1) = 0.f; sl.O(m, 2) = 0.f; sl.O(m, 3) = 0.f;
+    }
+  }
 }
 
 __global__ void __launch_bounds__(128, 1)
 k_solve(const SolverConfig cfg, const MpcProblemBatch batch, const MpcSolveOut out, const int B, int* __restrict__ work_counter) {
-  extern __shared__ float smem[];
-  float* ref = smem;
-  for (int i = threadIdx.x; i < kNRef * kRefStride; i += blockDim.x) ref[i] = c_ref[i];
-  __syncthreads();
-  Slots<float> sl{smem + kNRef * kRefStride + threadIdx.x, (int)blockDim.x, cfg.N, cfg.M};
+  extern __shared__ __align__(16) float smem[];
+  const RefTab<float> ref = stage_tables(smem);
+  Slots<float> sl{smem + kTabFloats + threadIdx.x, (int)blockDim.x, cfg.N, cfg.M};
   const unsigned full = 0xffffffffu;
 
   ProblemScalars<float> p;
@@ -130,11 +153,9 @@ cudaError_t launch_solve(const SolveLaunch& s, cudaStream_t stream) {
 __global__ void __launch_bounds__(64)
 k_rollout_cost(const SolverConfig cfg, const MpcProblemBatch batch, const int B, const float* __restrict__ U,
                float* __restrict__ X_out, float* __restrict__ cost6, float* __restrict__ total) {
-  extern __shared__ float smem[];
-  float* ref = smem;
-  for (int i = threadIdx.x; i < kNRef * kRefStride; i += blockDim.x) ref[i] = c_ref[i];
-  __syncthreads();
-  Slots<float> sl{smem + kNRef * kRefStride + threadIdx.x, (int)blockDim.x, cfg.N, cfg.M};
+  extern __shared__ __align__(16) float smem[];
+  const RefTab<float> ref = stage_tables(smem);
+  Slots<float> sl{smem + kTabFloats + threadIdx.x, (int)blockDim.x, cfg.N, cfg.M};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) {
     ProblemScalars<float> p;
     load_problem(batch, B, i, cfg, p, sl);
@@ -145,16 +166,16 @@ k_rollout_cost(const SolverConfig cfg, const MpcProblemBatch batch, const int B,
     float comp[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float J = rollout_nominal(cfg, p, ref, sl, comp);
     // final_state component (agents/pure_mpc.py:195-202: note the (y + y_ref) sign), reported only
-    int Jn = p.ego_index + cfg.N;
-    Jn = Jn < kNRef - 1 ? Jn : kNRef - 1;
-    const float* r = ref + Jn * kRefStride;
-    float ex = sl.X(cfg.N, 0) - r[0], ey = sl.X(cfg.N, 1) + r[1];
-    float ev = sl.X(cfg.N, 3) - ref_speed_at(p, cfg.N), eth = sl.X(cfg.N, 2) - r[2];
-    comp[2] = 100.f * (ex * ex + ey * ey + 20.f * ev * ev + eth * eth);
+    comp[2] = final_state_component(cfg, p, ref, sl);
     for (int c = 0; c < 6; ++c) cost6[(size_t)i * 6 + c] = comp[c];
     total[i] = J;
-    for (int k = 0; k <= cfg.N; ++k)
-      for (int c = 0; c < 4; ++c) X_out[((size_t)i * (cfg.N + 1) + k) * 4 + c] = sl.X(k, c);
+    for (int k = 0; k <= cfg.N; ++k) {
+      float* xo = X_out + ((size_t)i * (cfg.N + 1) + k) * 4;
+      xo[0] = (float)(p.x0 + (double)sl.X(k, 0));
+      xo[1] = (float)(p.y0 + (double)sl.X(k, 1));
+      xo[2] = sl.X(k, 2);
+      xo[3] = sl.X(k, 3);
+    }
   }
 }
 

@@ -38,14 +38,18 @@ def problems_from_obs(obs, ref_speed=None, has_ref_speed=None, w_distance=0.0, c
     return probs, agents
 
 
-def ref_speed_descriptor(rv):
-    """(vr_a, vr_slope, vr_b, vr_n) of a per-stage reference-speed profile (constant or ramp-then-zero)."""
+def ref_speed_descriptor(rv, rv_final=None):
+    """(vr_a, vr_slope, vr_b, vr_n) of a per-stage reference-speed profile (constant or ramp-then-zero).
+    `rv_final` is the value seen by stage N (only the reported final_state component uses it): a ramp
+    that is still running at stage N gets one more ramp point."""
     rv = np.asarray(rv, dtype=np.float64)
-    if np.all(rv == rv[0]):
+    if np.all(rv == rv[0]) and (rv_final is None or rv_final == rv[0]):
         return 0.0, 0.0, float(rv[0]), 0
     nz = np.nonzero(rv == 0)[0]
     n = int(nz[0]) if nz.size else len(rv)
     slope = float(rv[1] - rv[0]) if n > 1 else 0.0
+    if not nz.size and rv_final is not None and rv_final != 0.0:
+        n = len(rv) + 1
     return float(rv[0]), slope, 0.0, n
 
 
@@ -60,7 +64,7 @@ def batch_from_problems(probs, M):
         d["s0"][:, i] = p.s0
         d["ego_index"][i] = p.ego_index
         d["w_speed"][i], d["w_control"][i], d["w_diff"][i] = p.w_speed, p.w_control, p.w_input_diff
-        a, s, b, n = ref_speed_descriptor(p.ref_v)
+        a, s, b, n = ref_speed_descriptor(p.ref_v, p.ref_v_final)
         d["vr_a"][i], d["vr_slope"][i], d["vr_b"][i], d["vr_n"][i] = a, s, b, n
         d["is_collide"][i] = p.is_collide
         m = min(p.others.shape[0], M)
@@ -161,3 +165,18 @@ def oracle_warm_confirms(prob, U, du_tol=1e-3, rel_gain_tol=1e-6):
     du0 = float(np.max(np.abs(s.U[0] - U[0])))
     gain = float((c0 - s.cost) / (1.0 + abs(c0)))
     return (du0 < du_tol and gain < rel_gain_tol), du0, gain
+
+
+def distance_conditioning(prob, U, pos_err=2e-6, disc_band=1e-4):
+    """The distance term (1000|100)/(d+1e-6)^2 is discontinuous at d = 1 and ill-conditioned near
+    contact.  Returns (near_discontinuity, abs_tol): `near_discontinuity` when some |d - 1| < disc_band
+    (FP32 and FP64 may then sit on different branches -- a 900/d^2 jump); `abs_tol` = sum |phi'(d)| * pos_err,
+    the change of the un-weighted distance component caused by a position perturbation of pos_err metres
+    (FP32 rounding of a rollout over ~25 m)."""
+    if prob.others.shape[0] == 0:
+        return False, 0.0
+    X = orc.rollout(prob.s0, np.asarray(U, dtype=np.float64), prob.dt)
+    P = orc.obstacle_positions(prob.others, prob.N, prob.dt)
+    d = np.hypot(X[:prob.N, None, 0] - P[:, :, 0], X[:prob.N, None, 1] - P[:, :, 1])
+    c = np.where(d < 1.0, 1000.0, 100.0)
+    return bool(np.any(np.abs(d - 1.0) < disc_band)), float(np.sum(2.0 * c / (d + 1e-6) ** 3) * pos_err)

@@ -35,27 +35,45 @@ static void load_problem(const HsBatch& b, int B, int i, const SolverConfig& cfg
   p.w_control = T(b.w_control[i]);
   p.w_diff = T(b.w_diff[i]);
   p.vr_a = T(b.vr_a[i]); p.vr_slope = T(b.vr_slope[i]); p.vr_b = T(b.vr_b[i]); p.vr_n = b.vr_n[i];
-  for (int c = 0; c < 4; ++c) sl.X(0, c) = T(b.s0[(size_t)c * B + i]);
-  for (int m = 0; m < cfg.M; ++m)
-    for (int c = 0; c < 4; ++c) sl.O(m, c) = b.obstacles ? T(b.obstacles[((size_t)m * 4 + c) * B + i]) : T(0);
+  p.x0 = (double)b.s0[i];
+  p.y0 = (double)b.s0[(size_t)B + i];
+  sl.X(0, 0) = T(0); sl.X(0, 1) = T(0);
+  sl.X(0, 2) = T(b.s0[(size_t)2 * B + i]);
+  sl.X(0, 3) = T(b.s0[(size_t)3 * B + i]);
+  for (int m = 0; m < cfg.M; ++m) {
+    if (b.obstacles) {
+      sl.O(m, 0) = T((double)b.obstacles[((size_t)m * 4 + 0) * B + i] - p.x0);
+      sl.O(m, 1) = T((double)b.obstacles[((size_t)m * 4 + 1) * B + i] - p.y0);
+      sl.O(m, 2) = T(b.obstacles[((size_t)m * 4 + 2) * B + i]);
+      sl.O(m, 3) = T(b.obstacles[((size_t)m * 4 + 3) * B + i]);
+    } else {
+      for (int c = 0; c < 4; ++c) sl.O(m, c) = T(0);
+    }
+  }
 }
 
+template <typename T> struct HostTables {
+  std::vector<T> hsc;
+  std::vector<double> xy;
+  RefTab<T> tab() const { return RefTab<T>{hsc.data(), xy.data()}; }
+};
 template <typename T>
-static void make_ref(const double* ref85x4, std::vector<T>& out) {
-  out.resize(kNRef * kRefStride);
+static void make_ref(const double* ref85x4, HostTables<T>& out) {
+  out.hsc.resize(kNRef * kRefStride);
+  out.xy.resize(kNRef * 2);
   for (int j = 0; j < kNRef; ++j) {
-    out[j * 5 + 0] = T(ref85x4[j * 4 + 0]);
-    out[j * 5 + 1] = T(ref85x4[j * 4 + 1]);
-    out[j * 5 + 2] = T(ref85x4[j * 4 + 3]);
-    out[j * 5 + 3] = T(sin(ref85x4[j * 4 + 3]));
-    out[j * 5 + 4] = T(cos(ref85x4[j * 4 + 3]));
+    out.xy[2 * j] = ref85x4[j * 4 + 0];
+    out.xy[2 * j + 1] = ref85x4[j * 4 + 1];
+    out.hsc[j * kRefStride + 0] = T(ref85x4[j * 4 + 3]);
+    out.hsc[j * kRefStride + 1] = T(sin(ref85x4[j * 4 + 3]));
+    out.hsc[j * kRefStride + 2] = T(cos(ref85x4[j * 4 + 3]));
   }
 }
 
 template <typename T>
 static void run_solve(const SolverConfig& cfg, const double* ref, const HsBatch& b, int B, float* actions,
                       int* status, int* iters, float* cost, float* U_out, int* outer_out) {
-  std::vector<T> rt;
+  HostTables<T> rt;
   make_ref(ref, rt);
   std::vector<T> buf(slots_per_problem(cfg.N, cfg.M));
   for (int i = 0; i < B; ++i) {
@@ -63,7 +81,7 @@ static void run_solve(const SolverConfig& cfg, const double* ref, const HsBatch&
     ProblemScalars<T> p;
     load_problem(b, B, i, cfg, p, sl);
     SolveState<T> s;
-    solve_one(cfg, p, rt.data(), sl, s);
+    solve_one(cfg, p, rt.tab(), sl, s);
     actions[2 * i] = float(sl.U(0, 0));
     actions[2 * i + 1] = float(sl.U(0, 1));
     status[i] = s.status;
@@ -78,7 +96,7 @@ static void run_solve(const SolverConfig& cfg, const double* ref, const HsBatch&
 template <typename T>
 static void run_rollout_cost(const SolverConfig& cfg, const double* ref, const HsBatch& b, int B, const float* U,
                              const float* ref_v /*[N][B] or null*/, float* X_out, float* cost6, float* total) {
-  std::vector<T> rt;
+  HostTables<T> rt;
   make_ref(ref, rt);
   std::vector<T> buf(slots_per_problem(cfg.N, cfg.M));
   for (int i = 0; i < B; ++i) {
@@ -91,18 +109,15 @@ static void run_rollout_cost(const SolverConfig& cfg, const double* ref, const H
     }
     (void)ref_v;
     T comp[6] = {0, 0, 0, 0, 0, 0};
-    T J = rollout_nominal(cfg, p, rt.data(), sl, comp);
-    // final_state component (pure_mpc.py:195-202), reported never optimised
-    int Jn = p.ego_index + cfg.N;
-    Jn = Jn < kNRef - 1 ? Jn : kNRef - 1;
-    const T* r = rt.data() + Jn * kRefStride;
-    T ex = sl.X(cfg.N, 0) - r[0], ey = sl.X(cfg.N, 1) + r[1];
-    T ev = sl.X(cfg.N, 3) - ref_speed_at(p, cfg.N), eth = sl.X(cfg.N, 2) - r[2];
-    comp[2] = T(100) * (ex * ex + ey * ey + T(20) * ev * ev + eth * eth);
+    T J = rollout_nominal(cfg, p, rt.tab(), sl, comp);
+    comp[2] = final_state_component(cfg, p, rt.tab(), sl);
     for (int c = 0; c < 6; ++c) cost6[(size_t)i * 6 + c] = float(comp[c]);
     total[i] = float(J);
-    for (int k = 0; k <= cfg.N; ++k)
-      for (int c = 0; c < 4; ++c) X_out[((size_t)i * (cfg.N + 1) + k) * 4 + c] = float(sl.X(k, c));
+    for (int k = 0; k <= cfg.N; ++k) {
+      float* xo = X_out + ((size_t)i * (cfg.N + 1) + k) * 4;
+      xo[0] = float(p.x0 + double(sl.X(k, 0))); xo[1] = float(p.y0 + double(sl.X(k, 1)));
+      xo[2] = float(sl.X(k, 2)); xo[3] = float(sl.X(k, 3));
+    }
   }
 }
 
@@ -128,16 +143,16 @@ int hs_sizeof_config() { return (int)sizeof(SolverConfig); }
 // debugging aid: model-vs-actual merit along the DDP step from a given nominal U
 extern "C" int hs_linesearch_probe(const SolverConfig* cfg, const double* ref, const HsBatch* b, int B, int i, const float* U,
                                    double mu, int n_alpha, const double* alphas, double* out /* J0,d1,d2,J(a)... */) {
-  std::vector<double> rt;
+  HostTables<double> rt;
   make_ref(ref, rt);
   std::vector<double> buf(slots_per_problem(cfg->N, cfg->M));
   Slots<double> sl{buf.data(), 1, cfg->N, cfg->M};
   ProblemScalars<double> p;
   load_problem(*b, B, i, *cfg, p, sl);
   for (int k = 0; k < cfg->N; ++k) { sl.U(k, 0) = U[2 * k]; sl.U(k, 1) = U[2 * k + 1]; }
-  out[0] = rollout_nominal(*cfg, p, rt.data(), sl, (double*)nullptr);
-  backward_pass(*cfg, p, rt.data(), sl, mu, 1.0, &out[1], &out[2]);
-  for (int a = 0; a < n_alpha; ++a) { double md; out[3 + a] = forward_pass<double, false>(*cfg, p, rt.data(), sl, alphas[a], &md); }
+  out[0] = rollout_nominal(*cfg, p, rt.tab(), sl, (double*)nullptr);
+  backward_pass(*cfg, p, rt.tab(), sl, mu, 1.0, &out[1], &out[2]);
+  for (int a = 0; a < n_alpha; ++a) { double md; out[3 + a] = forward_pass<double, false>(*cfg, p, rt.tab(), sl, alphas[a], &md); }
   for (int k = 0; k < cfg->N; ++k) { out[3 + n_alpha + 2 * k] = sl.F(k, 0); out[3 + n_alpha + 2 * k + 1] = sl.F(k, 1); }
   return 0;
 }

@@ -1,0 +1,54 @@
+"""N > 1 host logic on CPU: env-index sharding and the all-gather of actions, world_size 2, gloo."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def test_shard_ranges_cover_the_batch():
+    from mpc_rl_for_avs_b200.sharding import shard_range
+    for total in (0, 1, 7, 65536, 1 << 20):
+        for world in (1, 2, 3, 8):
+            r = [shard_range(total, k, world) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == total
+            assert all(r[k][1] == r[k + 1][0] for k in range(world - 1))
+            sizes = [hi - lo for lo, hi in r]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(10, 2, 2)
+
+
+def _worker(rank, world, port, total, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mpc_rl_for_avs_b200.sharding import shard_range, all_gather_actions
+    lo, hi = shard_range(total, rank, world)
+    # "actions" of this shard: a known function of the global env index
+    idx = torch.arange(lo, hi, dtype=torch.float32)
+    local = torch.stack([idx, -2 * idx], dim=1)
+    full = all_gather_actions(local, total)
+    q.put((rank, full.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("total", [10, 11])
+def test_all_gather_actions_world2_gloo(total):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + total
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, total, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    idx = np.arange(total, dtype=np.float32)
+    exp = np.stack([idx, -2 * idx], axis=1)
+    for r in range(2):
+        assert np.array_equal(got[r], exp)
