@@ -105,6 +105,7 @@ MPC_API int mpc_create(const MpcConfig* cfg, int device, int max_batch, MpcHandl
   s.max_iter = cfg->max_iter > 0 ? cfg->max_iter : 60;
   s.tol_step = cfg->tol_step > 0.f ? cfg->tol_step : 1e-4f;
   s.reg_min = cfg->reg_min > 0.f ? cfg->reg_min : 1e-2f;
+  s.stall_tol = 1e-5f;
 
 #define CKC(call)                                                                        \
   do {                                                                                   \
@@ -114,9 +115,9 @@ MPC_API int mpc_create(const MpcConfig* cfg, int device, int max_batch, MpcHandl
 
   CKC(cudaSetDevice(device));
   // grid / block: as many problems resident per SM as the slot file allows
-  int tpb = cfg->threads_per_block > 0 ? cfg->threads_per_block : 128;
+  int tpb = cfg->threads_per_block > 0 ? cfg->threads_per_block : 192;
   tpb = (tpb + 31) / 32 * 32;
-  if (tpb > 128) tpb = 128;
+  if (tpb > 192) tpb = 192;
   while (tpb > 32 && solve_smem_bytes(N, M, tpb) > (size_t)h->smem_optin) tpb -= 32;
   if (solve_smem_bytes(N, M, tpb) > (size_t)h->smem_optin) { fail(nullptr, MPC_ERR_BAD_ARG, "mpc_create: horizon/obstacle count do not fit shared memory"); mpc_destroy(h); return MPC_ERR_BAD_ARG; }
   h->tpb = tpb;

@@ -24,6 +24,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define MPC_HD __host__ __device__ __forceinline__
@@ -81,6 +82,7 @@ struct SolverConfig {
   int max_iter;           // DDP iterations per problem (reference: ipopt.max_iter 1000, pure_mpc.py:294)
   float tol_step;         // convergence: max |du| of the accepted full step
   float reg_min;          // floor on |eigenvalue| of the regularised Quu
+  float stall_tol;        // relative objective decrease per 6 iterations below which a problem is declared stalled
 };
 
 // ---- per-problem scalars -------------------------------------------------------------
@@ -123,25 +125,73 @@ template <typename T> MPC_HD T ref_speed_at(const ProblemScalars<T>& p, int k) {
 
 // ---- strided slot file ----------------------------------------------------------------
 // base already points at this thread's lane; consecutive slots are `stride` apart.
-template <typename T> struct Slots {
+// Gains: the 2x6 feedback matrix and the feed-forward pair of a stage are only ever used as a
+// search direction (the step is validated by the line search on the exact objective), so on the
+// device they are stored as bf16 pairs -- 7 words per stage instead of 14.  That is what lets 192
+// instead of 128 problems stay resident per SM.  kPack = false keeps them in the scalar type
+// (host harness, double).
+MPC_HD uint32_t f2bf_bits(float f) {            // round-to-nearest-even float -> bf16 (finite inputs)
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  return (u + 0x7FFFu + ((u >> 16) & 1u)) >> 16;
+}
+MPC_HD float bf_bits2f(uint32_t h) {
+  uint32_t u = h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+template <typename T, bool kPack> struct Slots {
   T* base;
   int stride;
   int N, M;
   MPC_HD T& at(int s) const { return base[(long)s * stride]; }
+  static constexpr int kGainWords = kPack ? 7 : 14;
   // layout
   MPC_HD int oU() const { return 0; }                       // 2N
   MPC_HD int oX() const { return 2 * N; }                   // 4(N+1)
-  MPC_HD int oK() const { return 2 * N + 4 * (N + 1); }     // 12N
-  MPC_HD int oF() const { return oK() + 12 * N; }           // 2N feed-forward
-  MPC_HD int oO() const { return oF() + 2 * N; }            // 4M obstacles x,y,incx,incy
-  MPC_HD int total() const { return oO() + 4 * M; }
+  MPC_HD int oG() const { return 2 * N + 4 * (N + 1); }     // gains + feed-forward
+  MPC_HD int oO() const { return oG() + kGainWords * N; }   // 4M obstacles x,y,incx,incy
   MPC_HD T& U(int k, int i) const { return at(oU() + 2 * k + i); }
   MPC_HD T& X(int k, int i) const { return at(oX() + 4 * k + i); }
-  MPC_HD T& K(int k, int i) const { return at(oK() + 12 * k + i); }   // row-major 2x6
-  MPC_HD T& F(int k, int i) const { return at(oF() + 2 * k + i); }
   MPC_HD T& O(int m, int i) const { return at(oO() + 4 * m + i); }
+  // Kg[r][c]: rows (accel, steer), columns dz = (x, y, theta, v, a_prev, d_prev)
+  MPC_HD void store_gains(int k, T k0, T k1, const T (&Kg)[2][6]) const {
+    const int o = oG() + kGainWords * k;
+    if (kPack) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        uint32_t w = f2bf_bits(float(Kg[0][c])) | (f2bf_bits(float(Kg[1][c])) << 16);
+        memcpy(&at(o + c), &w, 4);
+      }
+      uint32_t w = f2bf_bits(float(k0)) | (f2bf_bits(float(k1)) << 16);
+      memcpy(&at(o + 6), &w, 4);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) { at(o + c) = Kg[0][c]; at(o + 6 + c) = Kg[1][c]; }
+      at(o + 12) = k0; at(o + 13) = k1;
+    }
+  }
+  MPC_HD void load_gains(int k, T& k0, T& k1, T (&Kr)[12]) const {
+    const int o = oG() + kGainWords * k;
+    if (kPack) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        uint32_t w;
+        memcpy(&w, &at(o + c), 4);
+        Kr[c] = T(bf_bits2f(w & 0xFFFFu)); Kr[6 + c] = T(bf_bits2f(w >> 16));
+      }
+      uint32_t w;
+      memcpy(&w, &at(o + 6), 4);
+      k0 = T(bf_bits2f(w & 0xFFFFu)); k1 = T(bf_bits2f(w >> 16));
+    } else {
+#pragma unroll
+      for (int c = 0; c < 12; ++c) Kr[c] = at(o + c);
+      k0 = at(o + 12); k1 = at(o + 13);
+    }
+  }
 };
-MPC_HD int slots_per_problem(int N, int M) { return 2 * N + 4 * (N + 1) + 12 * N + 2 * N + 4 * M; }
+MPC_HD int slots_per_problem(int N, int M, bool pack) { return 2 * N + 4 * (N + 1) + (pack ? 7 : 14) * N + 4 * M; }
 
 // ---- steering terms -------------------------------------------------------------------
 // beta = atan(0.5 tan delta) (pure_mpc.py:221) expressed without atan/tan:
@@ -179,9 +229,9 @@ MPC_HD void euler_step(T& x, T& y, T& th, T& v, T a, const Steer<T>& st, T dt, T
 // ---- stage cost (value only) ------------------------------------------------------------
 // comp[0..5] accumulate the reference's six un-weighted components (pure_mpc.py:215-216);
 // returns the weighted stage objective (pure_mpc.py:204-212 + archive terms).
-template <typename T>
+template <typename T, typename SL>
 MPC_HD T stage_cost(const SolverConfig& cfg, const ProblemScalars<T>& p, const RefTab<T>& ref,
-                    const Slots<T>& sl, int k, T x, T y, T th, T v, T a, T d, T ap, T dp, T* comp) {
+                    const SL& sl, int k, T x, T y, T th, T v, T a, T d, T ap, T dp, T* comp) {
   const RefPoint<T> r = ref_point(ref, p, k);
   T dx = x - r.x, dy = y - r.y;
   T perp = dx * r.sh - dy * r.ch;
@@ -250,9 +300,9 @@ template <typename T> MPC_HD Box<T> control_box(T th, T v, T dt) {
 // ---- open-loop rollout of the stored controls; fills X, returns the objective ----------------
 // Controls are used as stored (no clamping): this is also the parity entry point for
 // "rollout + six cost components" (mpc_rollout_cost).
-template <typename T>
+template <typename T, typename SL>
 MPC_HD T rollout_nominal(const SolverConfig& cfg, const ProblemScalars<T>& p, const RefTab<T>& ref,
-                         const Slots<T>& sl, T* comp /*6 or null*/) {
+                         const SL& sl, T* comp /*6 or null*/) {
   const int N = cfg.N;
   T x = sl.X(0, 0), y = sl.X(0, 1), th = sl.X(0, 2), v = sl.X(0, 3);
   T J = T(0), ap = T(0), dp = T(0);
@@ -269,8 +319,8 @@ MPC_HD T rollout_nominal(const SolverConfig& cfg, const ProblemScalars<T>& p, co
 
 // final_state component of the reference's cost_fn (agents/pure_mpc.py:195-202; note the
 // (y + y_ref) sign) -- reported, never optimised.  Needs absolute y: formed in FP64.
-template <typename T>
-MPC_HD T final_state_component(const SolverConfig& cfg, const ProblemScalars<T>& p, const RefTab<T>& ref, const Slots<T>& sl) {
+template <typename T, typename SL>
+MPC_HD T final_state_component(const SolverConfig& cfg, const ProblemScalars<T>& p, const RefTab<T>& ref, const SL& sl) {
   const int N = cfg.N;
   const RefPoint<T> r = ref_point(ref, p, N);
   int j = p.ego_index + N;
@@ -320,9 +370,9 @@ MPC_HD constexpr int sym6(int i, int j) { return i <= j ? (i * (13 - i)) / 2 + (
 // ---- backward pass -------------------------------------------------------------------------
 // Fills K (2x6 per stage) and F (feed-forward) from the nominal (X, U); returns the two
 // coefficients of the predicted objective change  dJ(alpha) = alpha*d1 + alpha^2*d2.
-template <typename T>
+template <typename T, typename SL>
 MPC_HD void backward_pass(const SolverConfig& cfg, const ProblemScalars<T>& p, const RefTab<T>& ref,
-                          const Slots<T>& sl, T mu, T hs, T* d1_out, T* d2_out) {
+                          const SL& sl, T mu, T hs, T* d1_out, T* d2_out) {
   // hs in [0,1] scales the second-order dynamics terms and the negative (tangential) obstacle
   // curvature: 0 = Gauss-Newton/iLQR model (robust far from the solution), 1 = exact Hessian.
   const int N = cfg.N;
@@ -548,9 +598,7 @@ MPC_HD void backward_pass(const SolverConfig& cfg, const ProblemScalars<T>& p, c
     printf("  k %d Quu %.4g %.4g %.4g Hdd %.4g Qu %.4g %.4g kff %.4g %.4g side %d %d box d [%.4g %.4g] sd %d %d P22 %.4g P33 %.4g p %.3g %.3g %.3g %.3g\n", k, (double)Quu00, (double)Quu01, (double)Quu11, (double)Hdd,
            (double)Qu[0], (double)Qu[1], (double)k0, (double)k1, s0, s1, (double)bx.lo_d, (double)bx.hi_d, (int)bx.sd_lo, (int)bx.sd_hi, (double)P[sym6(2,2)], (double)P[sym6(3,3)], (double)pv[0], (double)pv[1], (double)pv[2], (double)pv[3]);
 #endif
-    sl.F(k, 0) = k0; sl.F(k, 1) = k1;
-#pragma unroll
-    for (int jc = 0; jc < 6; ++jc) { sl.K(k, jc) = Kg[0][jc]; sl.K(k, 6 + jc) = Kg[1][jc]; }
+    sl.store_gains(k, k0, k1, Kg);
     // ---- predicted change and value update
     T Qk0 = E00 * k0 + E01 * k1, Qk1 = E01 * k0 + E11 * k1;
     d1 += k0 * Qu[0] + k1 * Qu[1];
@@ -575,40 +623,49 @@ MPC_HD void backward_pass(const SolverConfig& cfg, const ProblemScalars<T>& p, c
 }
 
 // ---- closed-loop forward pass -----------------------------------------------------------------
-// kCommit=false: evaluate the objective of step length alpha without touching the nominal.
-// kCommit=true : overwrite (X, U) in place with the new trajectory.  Returns the objective;
-// *maxdu = max |u_new - u_old| over the horizon.
-template <typename T, bool kCommit>
-MPC_HD T forward_pass(const SolverConfig& cfg, const ProblemScalars<T>& p, const RefTab<T>& ref,
-                      const Slots<T>& sl, T alpha, T* maxdu) {
+// Rolls the dynamics forward under the affine policy u = u_nom + alpha k + K dz, clamped to the
+// node's control box, for NA step lengths AT ONCE (independent dependency chains: the kernel is
+// latency bound, so the second candidate is almost free and the gains are loaded once).
+// commit (NA == 1 only): overwrite (X, U) in place with the new trajectory.
+// J[a] = objective, maxdu[a] = max |u_new - u_old| over the horizon.
+template <typename T, int NA, typename SL>
+MPC_HD void forward_pass(const SolverConfig& cfg, const ProblemScalars<T>& p, const RefTab<T>& ref,
+                         const SL& sl, const T* alpha, bool commit, T* J, T* maxdu) {
   const int N = cfg.N;
   const T dt = T(cfg.dt);
-  T x = sl.X(0, 0), y = sl.X(0, 1), th = sl.X(0, 2), v = sl.X(0, 3);
-  T J = T(0), ap = T(0), dp = T(0), dap = T(0), ddp = T(0), md = T(0);
-  for (int k = 0; k < N; ++k) {
-    T ex = x - sl.X(k, 0), ey = y - sl.X(k, 1), eth = th - sl.X(k, 2), ev = v - sl.X(k, 3);
-    T ua = sl.U(k, 0), ud = sl.U(k, 1);
-    T da = alpha * sl.F(k, 0) + sl.K(k, 0) * ex + sl.K(k, 1) * ey + sl.K(k, 2) * eth + sl.K(k, 3) * ev +
-           sl.K(k, 4) * dap + sl.K(k, 5) * ddp;
-    T dd = alpha * sl.F(k, 1) + sl.K(k, 6) * ex + sl.K(k, 7) * ey + sl.K(k, 8) * eth + sl.K(k, 9) * ev +
-           sl.K(k, 10) * dap + sl.K(k, 11) * ddp;
-    const Box<T> bx = control_box(th, v, dt);
-    T a = clamp_(ua + da, bx.lo_a, bx.hi_a);
-    T d = clamp_(ud + dd, bx.lo_d, bx.hi_d);
-    dap = a - ua; ddp = d - ud;
-    md = max_(md, max_(abs_(dap), abs_(ddp)));
-    J += stage_cost(cfg, p, ref, sl, k, x, y, th, v, a, d, ap, dp, (T*)nullptr);
-    if (kCommit) {
-      sl.X(k, 0) = x; sl.X(k, 1) = y; sl.X(k, 2) = th; sl.X(k, 3) = v;
-      sl.U(k, 0) = a; sl.U(k, 1) = d;
-    }
-    Steer<T> st = steer_terms(d, false);
-    euler_step(x, y, th, v, a, st, dt);
-    ap = a; dp = d;
+  T x[NA], y[NA], th[NA], v[NA], ap[NA], dp[NA], dap[NA], ddp[NA];
+#pragma unroll
+  for (int a = 0; a < NA; ++a) {
+    x[a] = sl.X(0, 0); y[a] = sl.X(0, 1); th[a] = sl.X(0, 2); v[a] = sl.X(0, 3);
+    ap[a] = dp[a] = dap[a] = ddp[a] = T(0);
+    J[a] = T(0); maxdu[a] = T(0);
   }
-  if (kCommit) { sl.X(N, 0) = x; sl.X(N, 1) = y; sl.X(N, 2) = th; sl.X(N, 3) = v; }
-  *maxdu = md;
-  return J;
+  for (int k = 0; k < N; ++k) {
+    const T xn = sl.X(k, 0), yn = sl.X(k, 1), thn = sl.X(k, 2), vn = sl.X(k, 3);
+    const T ua = sl.U(k, 0), ud = sl.U(k, 1);
+    T f0, f1, Kr[12];
+    sl.load_gains(k, f0, f1, Kr);
+#pragma unroll
+    for (int a = 0; a < NA; ++a) {
+      const T ex = x[a] - xn, ey = y[a] - yn, eth = th[a] - thn, ev = v[a] - vn;
+      const T da = alpha[a] * f0 + Kr[0] * ex + Kr[1] * ey + Kr[2] * eth + Kr[3] * ev + Kr[4] * dap[a] + Kr[5] * ddp[a];
+      const T dd = alpha[a] * f1 + Kr[6] * ex + Kr[7] * ey + Kr[8] * eth + Kr[9] * ev + Kr[10] * dap[a] + Kr[11] * ddp[a];
+      const Box<T> bx = control_box(th[a], v[a], dt);
+      const T ac = clamp_(ua + da, bx.lo_a, bx.hi_a);
+      const T dc = clamp_(ud + dd, bx.lo_d, bx.hi_d);
+      dap[a] = ac - ua; ddp[a] = dc - ud;
+      maxdu[a] = max_(maxdu[a], max_(abs_(dap[a]), abs_(ddp[a])));
+      J[a] += stage_cost(cfg, p, ref, sl, k, x[a], y[a], th[a], v[a], ac, dc, ap[a], dp[a], (T*)nullptr);
+      if (NA == 1 && commit) {
+        sl.X(k, 0) = x[a]; sl.X(k, 1) = y[a]; sl.X(k, 2) = th[a]; sl.X(k, 3) = v[a];
+        sl.U(k, 0) = ac; sl.U(k, 1) = dc;
+      }
+      Steer<T> st = steer_terms(dc, false);
+      euler_step(x[a], y[a], th[a], v[a], ac, st, dt);
+      ap[a] = ac; dp[a] = dc;
+    }
+  }
+  if (NA == 1 && commit) { sl.X(N, 0) = x[0]; sl.X(N, 1) = y[0]; sl.X(N, 2) = th[0]; sl.X(N, 3) = v[0]; }
 }
 
 // status bits returned per problem
@@ -617,25 +674,28 @@ enum : int {
   kStatusMaxIter = 1,        // iteration cap hit (the iterate is still returned, like the reference's print-only failure path pure_mpc.py:303-305)
   kStatusLineSearchFail = 2, // no acceptable step at maximum regularisation
   kStatusNaN = 4,
-  kStatusInfeasibleStart = 8 // s0 violates a state bound (the reference NLP is infeasible)
+  kStatusInfeasibleStart = 8, // s0 violates a state bound (the reference NLP is infeasible)
+  kStatusStalled = 16         // objective stopped improving (relative change < stall_tol over a window) without the step test passing
 };
 
 // ---- per-thread solver state -------------------------------------------------------------------
 template <typename T> struct SolveState {
   T J, mu, hs;
-  int iter, status;
+  T J_mark;               // objective at the last progress checkpoint
+  int iter, status, trials;
   bool done;
 };
 
-template <typename T>
+template <typename T, typename SL>
 MPC_HD void solve_begin(const SolverConfig& cfg, const ProblemScalars<T>& p, const RefTab<T>& ref,
-                        const Slots<T>& sl, SolveState<T>& s) {
+                        const SL& sl, SolveState<T>& s) {
   for (int k = 0; k < cfg.N; ++k) { sl.U(k, 0) = T(0); sl.U(k, 1) = T(0); }   // cold start (pure_mpc.py:244)
   s.mu = T(0); s.hs = T(1);
-  s.iter = 0; s.status = 0; s.done = false;
+  s.iter = 0; s.status = 0; s.trials = 0; s.done = false;
   T v0 = sl.X(0, 3), th0 = sl.X(0, 2);
   if (v0 < Lim<T>::v_min() || v0 > Lim<T>::v_max() || abs_(th0) > Lim<T>::th_max() * T(1.000001)) s.status |= kStatusInfeasibleStart;
   s.J = rollout_nominal(cfg, p, ref, sl, (T*)nullptr);
+  s.J_mark = s.J;
 }
 
 template <typename T> struct Eps;
@@ -653,7 +713,8 @@ template <typename T> MPC_HD bool accept_step(T J, T Jn, T expected) {
   return (expected > -noise) && (Jn <= J + noise);
 }
 
-constexpr int kMaxLineSearch = 8;      // alpha = 1, 1/2, ..., 1/128
+constexpr int kLineSearchPasses = 2;   // two candidates per pass: alpha = (1, 1/2), then (1/4, 1/8)
+constexpr int kStallWindow = 6;        // iterations between progress checkpoints
 
 // bookkeeping after a line search; sets s.done when converged or failed.
 template <typename T>
@@ -667,26 +728,44 @@ MPC_HD void after_line_search(const SolverConfig& cfg, SolveState<T>& s, bool ac
     s.mu = max_(s.mu * T(10), T(0.1));
     if (s.mu > T(1e9)) { s.status |= kStatusLineSearchFail; s.done = true; }
   }
+  if (!s.done && s.iter % kStallWindow == 0) {
+    // progress checkpoint: problems that sit on a kink of the clamped dynamics keep taking tiny or
+    // rejected steps; they end here instead of burning the iteration cap
+    if (s.J_mark - s.J <= T(cfg.stall_tol) * (abs_(s.J) + T(1))) { s.status |= kStatusStalled; s.done = true; }
+    s.J_mark = s.J;
+  }
   if (!s.done && s.iter >= cfg.max_iter) { s.status |= kStatusMaxIter; s.done = true; }
+}
+
+// one line-search pass: tries alpha and alpha/2 together.  On success `alpha` holds the accepted step
+// length; otherwise it is divided by 4 for the next pass.
+template <typename T, typename SL>
+MPC_HD bool line_search_pass(const SolverConfig& cfg, const ProblemScalars<T>& p, const RefTab<T>& ref,
+                             const SL& sl, SolveState<T>& s, T d1, T d2, T& alpha) {
+  T al[2] = {alpha, alpha * T(0.5)}, Jt[2], mt[2];
+  forward_pass<T, 2, SL>(cfg, p, ref, sl, al, false, Jt, mt);
+  s.trials += 2;
+  if (accept_step(s.J, Jt[0], al[0] * d1 + al[0] * al[0] * d2)) { alpha = al[0]; return true; }
+  if (accept_step(s.J, Jt[1], al[1] * d1 + al[1] * al[1] * d2)) { alpha = al[1]; return true; }
+  alpha = alpha * T(0.25);
+  return false;
 }
 
 // straight-line single-problem driver (host harness; the kernel runs the same sub-steps with
 // a warp-synchronous line search, see mpc_kernels.cu)
-template <typename T>
+template <typename T, typename SL>
 MPC_HD void solve_one(const SolverConfig& cfg, const ProblemScalars<T>& p, const RefTab<T>& ref,
-                      const Slots<T>& sl, SolveState<T>& s) {
+                      const SL& sl, SolveState<T>& s) {
   solve_begin(cfg, p, ref, sl, s);
   while (!s.done) {
     T d1, d2;
     backward_pass(cfg, p, ref, sl, s.mu, s.hs, &d1, &d2);
     T alpha = T(1), Jn = T(0), md = T(0);
     bool acc = false;
-    for (int t = 0; t < kMaxLineSearch && !acc; ++t) {
-      Jn = forward_pass<T, false>(cfg, p, ref, sl, alpha, &md);
-      acc = accept_step(s.J, Jn, alpha * d1 + alpha * alpha * d2);
-      if (!acc) alpha *= T(0.5);
+    for (int t = 0; t < kLineSearchPasses && !acc; ++t) {
+      acc = line_search_pass(cfg, p, ref, sl, s, d1, d2, alpha);
     }
-    if (acc) Jn = forward_pass<T, true>(cfg, p, ref, sl, alpha, &md);
+    if (acc) forward_pass<T, 1, SL>(cfg, p, ref, sl, &alpha, true, &Jn, &md);
 #if defined(MPC_TRACE) && !defined(__CUDA_ARCH__)
     printf("it %d J %.9g d1 %.4g d2 %.4g alpha %.4g acc %d Jn %.9g maxdu %.3g mu %.3g hs %g u0 %.6f %.6f\n", s.iter, (double)s.J,
            (double)d1, (double)d2, (double)alpha, (int)acc, (double)Jn, (double)md, (double)s.mu, (double)s.hs, (double)sl.U(0, 0), (double)sl.U(0, 1));

@@ -4,10 +4,10 @@
 //   * one problem per THREAD.  The horizon recursion (rollout, Riccati sweep) is serial in k and
 //     the per-stage blocks are 6x6 / 2x6 -- nothing a warp or a tensor core could share -- so the
 //     parallelism that exists is across problems and lanes stay full for the dominant work.
-//   * the per-problem horizon arrays (U, X, gains, feed-forward, obstacle tracks: 436 floats at
-//     H=20, M=8) live in a strided shared-memory slot file (slot*blockDim + tid: bank-conflict
+//   * the per-problem horizon arrays (U, X, bf16-packed gains + feed-forward, obstacle tracks:
+//     296 words at H=20, M=8) live in a strided shared-memory slot file (slot*blockDim + tid: bank-conflict
 //     free), the value-function block (21+6 floats) in registers.  Shared memory, not registers,
-//     bounds residency: 128 problems / SM.
+//     bounds residency: 192 problems / SM.
 //   * persistent grid (blocks = SMs x blocks/SM).  Iteration counts differ by 10x between
 //     problems, so a thread that finishes pulls the next problem index from a global counter
 //     instead of idling until its warp's slowest problem ends.
@@ -40,7 +40,7 @@ cudaError_t upload_ref_table_solve() {
 
 constexpr int kTabFloats = kNRef * 2 * 2 + kNRef * kRefStride + 1;   // FP64 xy (as 2 floats each) + hsc, padded to even
 size_t solve_smem_bytes(int N, int M, int tpb) {
-  return (size_t)(kTabFloats + slots_per_problem(N, M) * tpb) * sizeof(float);
+  return (size_t)(kTabFloats + slots_per_problem(N, M, true) * tpb) * sizeof(float);
 }
 
 // block-shared copy of the path tables at the head of dynamic shared memory
@@ -54,7 +54,7 @@ __device__ __forceinline__ RefTab<float> stage_tables(float* smem) {
 }
 
 __device__ __forceinline__ void load_problem(const MpcProblemBatch& b, int B, int i, const SolverConfig& cfg,
-                                             ProblemScalars<float>& p, const Slots<float>& sl) {
+                                             ProblemScalars<float>& p, const Slots<float, true>& sl) {
   p.ego_index = b.ego_index[i];
   int n = b.n_obs ? b.n_obs[i] : 0;
   p.n_obs = n < cfg.M ? n : cfg.M;
@@ -83,11 +83,11 @@ __device__ __forceinline__ void load_problem(const MpcProblemBatch& b, int B, in
   }
 }
 
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(192, 1)
 k_solve(const SolverConfig cfg, const MpcProblemBatch batch, const MpcSolveOut out, const int B, int* __restrict__ work_counter) {
   extern __shared__ __align__(16) float smem[];
   const RefTab<float> ref = stage_tables(smem);
-  Slots<float> sl{smem + kTabFloats + threadIdx.x, (int)blockDim.x, cfg.N, cfg.M};
+  Slots<float, true> sl{smem + kTabFloats + threadIdx.x, (int)blockDim.x, cfg.N, cfg.M};
   const unsigned full = 0xffffffffu;
 
   ProblemScalars<float> p;
@@ -110,16 +110,12 @@ k_solve(const SolverConfig cfg, const MpcProblemBatch batch, const MpcSolveOut o
     if (active) backward_pass(cfg, p, ref, sl, s.mu, s.hs, &d1, &d2);
     float alpha = 1.f, Jn = 0.f, md = 0.f;
     bool acc = false;
-    for (int t = 0; t < kMaxLineSearch; ++t) {
+    for (int t = 0; t < kLineSearchPasses; ++t) {
       const bool need = active && !acc;
       if (!__any_sync(full, need)) break;
-      if (need) {
-        Jn = forward_pass<float, false>(cfg, p, ref, sl, alpha, &md);
-        acc = accept_step(s.J, Jn, alpha * d1 + alpha * alpha * d2);
-        if (!acc) alpha *= 0.5f;
-      }
+      if (need) acc = line_search_pass(cfg, p, ref, sl, s, d1, d2, alpha);
     }
-    if (active && acc) Jn = forward_pass<float, true>(cfg, p, ref, sl, alpha, &md);
+    if (active && acc) forward_pass<float, 1, Slots<float, true>>(cfg, p, ref, sl, &alpha, true, &Jn, &md);
     if (active) {
       after_line_search(cfg, s, acc, alpha, Jn, md);
       if (s.done) {
@@ -155,7 +151,7 @@ k_rollout_cost(const SolverConfig cfg, const MpcProblemBatch batch, const int B,
                float* __restrict__ X_out, float* __restrict__ cost6, float* __restrict__ total) {
   extern __shared__ __align__(16) float smem[];
   const RefTab<float> ref = stage_tables(smem);
-  Slots<float> sl{smem + kTabFloats + threadIdx.x, (int)blockDim.x, cfg.N, cfg.M};
+  Slots<float, true> sl{smem + kTabFloats + threadIdx.x, (int)blockDim.x, cfg.N, cfg.M};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) {
     ProblemScalars<float> p;
     load_problem(batch, B, i, cfg, p, sl);

@@ -88,7 +88,7 @@ def problem_f32(p):
 class HsConfig(C.Structure):       # mirrors mpcb::SolverConfig
     _fields_ = [("N", C.c_int), ("M", C.c_int), ("dt", C.c_float), ("w_distance", C.c_float),
                 ("w_collision", C.c_float), ("literal_no_collision", C.c_int), ("max_iter", C.c_int),
-                ("tol_step", C.c_float), ("reg_min", C.c_float)]
+                ("tol_step", C.c_float), ("reg_min", C.c_float), ("stall_tol", C.c_float)]
 
 
 _P = C.POINTER
@@ -101,9 +101,9 @@ class HsBatch(C.Structure):
                 ("is_collide", _P(C.c_ubyte)), ("n_obs", _P(C.c_int)), ("obstacles", _P(C.c_float))]
 
 
-def hs_config(N=20, M=8, dt=0.1, w_distance=0.0, w_collision=0.0, literal=0, max_iter=60, tol_step=1e-4, reg_min=1e-2):
+def hs_config(N=20, M=8, dt=0.1, w_distance=0.0, w_collision=0.0, literal=0, max_iter=60, tol_step=1e-4, reg_min=1e-2, stall_tol=1e-5):
     return HsConfig(N=N, M=M, dt=dt, w_distance=w_distance, w_collision=w_collision, literal_no_collision=literal,
-                    max_iter=max_iter, tol_step=tol_step, reg_min=reg_min)
+                    max_iter=max_iter, tol_step=tol_step, reg_min=reg_min, stall_tol=stall_tol)
 
 
 def load_hostsim():

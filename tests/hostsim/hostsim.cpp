@@ -25,8 +25,8 @@ struct HsBatch {               // same SoA layout as MpcProblemBatch (include/mp
   const float* obstacles;      // [M][4][B]
 };
 
-template <typename T>
-static void load_problem(const HsBatch& b, int B, int i, const SolverConfig& cfg, ProblemScalars<T>& p, Slots<T>& sl) {
+template <typename T, typename SL>
+static void load_problem(const HsBatch& b, int B, int i, const SolverConfig& cfg, ProblemScalars<T>& p, SL& sl) {
   p.ego_index = b.ego_index[i];
   p.n_obs = b.n_obs ? b.n_obs[i] : 0;
   if (p.n_obs > cfg.M) p.n_obs = cfg.M;
@@ -70,14 +70,14 @@ static void make_ref(const double* ref85x4, HostTables<T>& out) {
   }
 }
 
-template <typename T>
+template <typename T, bool kPack>
 static void run_solve(const SolverConfig& cfg, const double* ref, const HsBatch& b, int B, float* actions,
                       int* status, int* iters, float* cost, float* U_out, int* outer_out) {
   HostTables<T> rt;
   make_ref(ref, rt);
-  std::vector<T> buf(slots_per_problem(cfg.N, cfg.M));
+  std::vector<T> buf(slots_per_problem(cfg.N, cfg.M, kPack));
   for (int i = 0; i < B; ++i) {
-    Slots<T> sl{buf.data(), 1, cfg.N, cfg.M};
+    Slots<T, kPack> sl{buf.data(), 1, cfg.N, cfg.M};
     ProblemScalars<T> p;
     load_problem(b, B, i, cfg, p, sl);
     SolveState<T> s;
@@ -86,7 +86,7 @@ static void run_solve(const SolverConfig& cfg, const double* ref, const HsBatch&
     actions[2 * i + 1] = float(sl.U(0, 1));
     status[i] = s.status;
     iters[i] = s.iter;
-    if (outer_out) outer_out[i] = 0;
+    if (outer_out) outer_out[i] = s.trials;
     cost[i] = float(s.J);
     if (U_out)
       for (int k = 0; k < cfg.N; ++k) { U_out[((size_t)i * cfg.N + k) * 2] = float(sl.U(k, 0)); U_out[((size_t)i * cfg.N + k) * 2 + 1] = float(sl.U(k, 1)); }
@@ -98,9 +98,9 @@ static void run_rollout_cost(const SolverConfig& cfg, const double* ref, const H
                              const float* ref_v /*[N][B] or null*/, float* X_out, float* cost6, float* total) {
   HostTables<T> rt;
   make_ref(ref, rt);
-  std::vector<T> buf(slots_per_problem(cfg.N, cfg.M));
+  std::vector<T> buf(slots_per_problem(cfg.N, cfg.M, false));
   for (int i = 0; i < B; ++i) {
-    Slots<T> sl{buf.data(), 1, cfg.N, cfg.M};
+    Slots<T, false> sl{buf.data(), 1, cfg.N, cfg.M};
     ProblemScalars<T> p;
     load_problem(b, B, i, cfg, p, sl);
     for (int k = 0; k < cfg.N; ++k) {
@@ -125,8 +125,11 @@ extern "C" {
 
 int hs_solve(const SolverConfig* cfg, const double* ref85x4, const HsBatch* b, int B, int use_double, float* actions,
              int* status, int* iters, float* cost, float* U_out, int* outer_out) {
-  if (use_double) run_solve<double>(*cfg, ref85x4, *b, B, actions, status, iters, cost, U_out, outer_out);
-  else run_solve<float>(*cfg, ref85x4, *b, B, actions, status, iters, cost, U_out, outer_out);
+  // use_double: 1 = double; 0 = float with bf16-packed gains (exactly the device arithmetic);
+  // 2 = float with full-precision gains (to isolate the effect of the packing)
+  if (use_double == 1) run_solve<double, false>(*cfg, ref85x4, *b, B, actions, status, iters, cost, U_out, outer_out);
+  else if (use_double == 2) run_solve<float, false>(*cfg, ref85x4, *b, B, actions, status, iters, cost, U_out, outer_out);
+  else run_solve<float, true>(*cfg, ref85x4, *b, B, actions, status, iters, cost, U_out, outer_out);
   return 0;
 }
 
@@ -145,14 +148,14 @@ extern "C" int hs_linesearch_probe(const SolverConfig* cfg, const double* ref, c
                                    double mu, int n_alpha, const double* alphas, double* out /* J0,d1,d2,J(a)... */) {
   HostTables<double> rt;
   make_ref(ref, rt);
-  std::vector<double> buf(slots_per_problem(cfg->N, cfg->M));
-  Slots<double> sl{buf.data(), 1, cfg->N, cfg->M};
+  std::vector<double> buf(slots_per_problem(cfg->N, cfg->M, false));
+  Slots<double, false> sl{buf.data(), 1, cfg->N, cfg->M};
   ProblemScalars<double> p;
   load_problem(*b, B, i, *cfg, p, sl);
   for (int k = 0; k < cfg->N; ++k) { sl.U(k, 0) = U[2 * k]; sl.U(k, 1) = U[2 * k + 1]; }
   out[0] = rollout_nominal(*cfg, p, rt.tab(), sl, (double*)nullptr);
   backward_pass(*cfg, p, rt.tab(), sl, mu, 1.0, &out[1], &out[2]);
-  for (int a = 0; a < n_alpha; ++a) { double md; out[3 + a] = forward_pass<double, false>(*cfg, p, rt.tab(), sl, alphas[a], &md); }
-  for (int k = 0; k < cfg->N; ++k) { out[3 + n_alpha + 2 * k] = sl.F(k, 0); out[3 + n_alpha + 2 * k + 1] = sl.F(k, 1); }
+  for (int a = 0; a < n_alpha; ++a) { double md, al = alphas[a]; forward_pass<double, 1>(*cfg, p, rt.tab(), sl, &al, false, &out[3 + a], &md); }
+  for (int k = 0; k < cfg->N; ++k) { double f0, f1, Kr[12]; sl.load_gains(k, f0, f1, Kr); out[3 + n_alpha + 2 * k] = f0; out[3 + n_alpha + 2 * k + 1] = f1; }
   return 0;
 }
