@@ -143,7 +143,10 @@ def main() -> None:
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     total = B * world
-    agent = pkg.BatchedPureMPC(CFG, vehicles_count=M + 1, max_batch=B, device=local, collision_check=True, weight_distance=W_DIST)
+    tune = {k: int(os.environ[e]) for k, e in (("max_iter", "MPC_MAX_ITER"), ("threads_per_block", "MPC_TPB"),
+                                                ("blocks_per_sm", "MPC_BPS")) if e in os.environ}      # experiments only
+    agent = pkg.BatchedPureMPC(CFG, vehicles_count=M + 1, max_batch=B, device=local, collision_check=True,
+                               weight_distance=W_DIST, **tune)
 
     nsteps = args.warmup + args.steps
     # distinct batches per step; inputs live in HBM before the timed region (value) and in pinned host

@@ -47,14 +47,40 @@ template <typename T> struct Lim {
 };
 
 // ---- scalar math dispatch ---------------------------------------------------------
-MPC_HD void sincos_(float x, float* s, float* c) {
-#if defined(__CUDA_ARCH__)
-  sincosf(x, s, c);
+#if defined(__CUDACC__)
+#define MPC_NOINLINE __host__ __device__ __noinline__
 #else
-  *s = sinf(x); *c = cosf(x);
+#define MPC_NOINLINE __attribute__((noinline))
 #endif
+
+// sin and cos for |x| <= ~4 rad (headings live in [-pi, pi] plus one Euler step, steering in
+// [-pi/3, pi/3]): one Cody-Waite step to |r| <= pi/4 and the Cephes single-precision kernels
+// (~1 ulp).  The general-purpose sincosf drags a Payne-Hanek slow path into every call site and
+// the kernel is instruction-cache bound, so the lean version is worth ~10% of the code size.
+MPC_HD void sincos_(float x, float* s, float* c) {
+  const float kf = rintf(x * 0.636619772367581343f);           // nearest multiple of pi/2
+  float r = fmaf(-kf, 1.57079601287841796875f, x);             // pi/2 split hi / lo
+  r = fmaf(-kf, 3.1391647326017846353352069854736e-7f, r);
+  const float z = r * r;
+  const float sp = r + r * z * fmaf(z, fmaf(z, -1.9515295891e-4f, 8.3321608736e-3f), -1.6666654611e-1f);
+  const float cp = fmaf(z * z, fmaf(z, fmaf(z, 2.443315711809948e-5f, -1.388731625493765e-3f), 4.166664568298827e-2f),
+                        fmaf(-0.5f, z, 1.0f));
+  const int q = (int)kf & 3;
+  const float ss = (q & 1) ? cp : sp, cc = (q & 1) ? sp : cp;
+  *s = (q & 2) ? -ss : ss;
+  *c = ((q + 1) & 2) ? -cc : cc;
 }
 MPC_HD void sincos_(double x, double* s, double* c) { *s = sin(x); *c = cos(x); }
+// 1/x and a/b: the device path uses the 2-ulp hardware approximations (MUFU + no slow path);
+// every quantity they touch is either a search direction or carries 1e-5 relative tolerance
+MPC_HD float rcp_(float x) {
+#if defined(__CUDA_ARCH__)
+  return __fdividef(1.0f, x);
+#else
+  return 1.0f / x;
+#endif
+}
+MPC_HD double rcp_(double x) { return 1.0 / x; }
 MPC_HD float rsqrt_(float x) {
 #if defined(__CUDA_ARCH__)
   return rsqrtf(x);
@@ -145,7 +171,7 @@ template <typename T, bool kPack> struct Slots {
   T* base;
   int stride;
   int N, M;
-  MPC_HD T& at(int s) const { return base[(long)s * stride]; }
+  MPC_HD T& at(int s) const { return base[(unsigned)s * (unsigned)stride]; }
   static constexpr int kGainWords = kPack ? 7 : 14;
   // layout
   MPC_HD int oU() const { return 0; }                       // 2N
@@ -206,7 +232,7 @@ template <typename T> MPC_HD Steer<T> steer_terms(T delta, bool second) {
   Steer<T> o;
   o.cb = cd * r;
   o.sb = T(0.5) * sd * r;
-  T iq = T(1) / q;
+  T iq = rcp_(q);
   o.g = T(0.5) * iq;
   o.h = second ? T(0.75) * sd * cd * iq * iq : T(0);
   return o;
@@ -247,11 +273,11 @@ MPC_HD T stage_cost(const SolverConfig& cfg, const ProblemScalars<T>& p, const R
     for (int m = 0; m < p.n_obs; ++m) {
       T ex = x - (sl.O(m, 0) + T(k) * sl.O(m, 2));
       T ey = y - (sl.O(m, 1) + T(k) * sl.O(m, 3));
-      T d2 = ex * ex + ey * ey;
-      T dd = sqrt_(d2);
-      T e = dd + T(1e-6);
+      T d2 = ex * ex + ey * ey + T(1e-30);
+      T dd = d2 * rsqrt_(d2);
+      T ie = rcp_(dd + T(1e-6));
       T c = dd < T(1) ? T(1000) : T(100);
-      dist += c / (e * e);
+      dist += c * ie * ie;
     }
   }
   T col = p.is_collide ? T(3000) * v * v : T(0);
@@ -275,7 +301,9 @@ template <typename T> MPC_HD T sb_max() { return T(0.6546536707079771); }   // s
 MPC_HD float asin_(float x) { return asinf(x); }
 MPC_HD double asin_(double x) { return asin(x); }
 // inverse of sin beta(delta) = 0.5 sin d / sqrt(1 - 0.75 sin^2 d)
-template <typename T> MPC_HD T delta_of_sinbeta(T sb) {
+// (rarely executed: only when a node sits within one step of the heading bound -- kept out of line
+// so that asinf is not inlined at every call site of control_box)
+template <typename T> MPC_NOINLINE T delta_of_sinbeta(T sb) {
   sb = clamp_(sb, -sb_max<T>(), sb_max<T>());
   return asin_(sb * rsqrt_(T(0.25) + T(0.75) * sb * sb));
 }
@@ -284,7 +312,7 @@ template <typename T> MPC_HD Box<T> control_box(T th, T v, T dt) {
   b.lo_a = -Lim<T>::a_max(); b.hi_a = Lim<T>::a_max();
   b.lo_d = -Lim<T>::d_max(); b.hi_d = Lim<T>::d_max();
   b.sa_lo = b.sa_hi = b.sd_lo = b.sd_hi = false;
-  const T idt = T(1) / dt;
+  const T idt = rcp_(dt);
   T ha = (Lim<T>::v_max() - v) * idt, la = (Lim<T>::v_min() - v) * idt;
   if (ha < b.hi_a) { b.hi_a = ha; b.sa_hi = true; }
   if (la > b.lo_a) { b.lo_a = la; b.sa_lo = true; }
@@ -336,13 +364,13 @@ MPC_HD T final_state_component(const SolverConfig& cfg, const ProblemScalars<T>&
 // inside, otherwise the best of the four edge minimisers.  side[i] = 0 free, -1 at lo, +1 at hi.
 template <typename T>
 MPC_HD void box_qp2(T h00, T h01, T h11, T g0, T g1, T lo0, T hi0, T lo1, T hi1, T* d0, T* d1, int* side0, int* side1) {
-  T idet = T(1) / (h00 * h11 - h01 * h01);
+  T idet = rcp_(h00 * h11 - h01 * h01);
   T n0 = -(h11 * g0 - h01 * g1) * idet;
   T n1 = -(h00 * g1 - h01 * g0) * idet;
   if (n0 >= lo0 && n0 <= hi0 && n1 >= lo1 && n1 <= hi1) { *d0 = n0; *d1 = n1; *side0 = 0; *side1 = 0; return; }
   T best = T(1e30), b0 = T(0), b1 = T(0);
   int s0 = 0, s1 = 0;
-  const T ih11 = T(1) / h11, ih00 = T(1) / h00;
+  const T ih11 = rcp_(h11), ih00 = rcp_(h00);
 #pragma unroll
   for (int e = 0; e < 2; ++e) {          // coordinate 0 pinned to an edge
     T f0 = e ? hi0 : lo0;
@@ -421,13 +449,12 @@ MPC_HD void backward_pass(const SolverConfig& cfg, const ProblemScalars<T>& p, c
         for (int m = 0; m < p.n_obs; ++m) {
           T ex = x - (sl.O(m, 0) + T(k) * sl.O(m, 2));
           T ey = y - (sl.O(m, 1) + T(k) * sl.O(m, 3));
-          T d2_ = ex * ex + ey * ey;
-          T dd = sqrt_(d2_);
-          T e = dd + T(1e-6);
+          T d2_ = ex * ex + ey * ey + T(1e-30);
+          T idd = rsqrt_(d2_);
+          T dd = d2_ * idd;
           T cw = wd * (dd < T(1) ? T(1000) : T(100));
-          T ie = T(1) / e;
+          T ie = rcp_(dd + T(1e-6));
           T ie2 = ie * ie;
-          T idd = T(1) / max_(dd, T(1e-12));
           T f1 = -T(2) * cw * ie2 * ie;          // phi'(d)
           T f2 = T(6) * cw * ie2 * ie2;          // phi''(d)
           T nx = ex * idd, ny = ey * idd;
@@ -529,7 +556,7 @@ MPC_HD void backward_pass(const SolverConfig& cfg, const ProblemScalars<T>& p, c
       T l1 = hm - rr, l2 = hm + rr;
       T n1 = max_(abs_(l1), T(cfg.reg_min)), n2 = max_(abs_(l2), T(cfg.reg_min));
       if (rr > T(1e-12) * (abs_(hm) + T(1e-30))) {
-        T i2r = T(0.5) / rr;
+        T i2r = T(0.5) * rcp_(rr);
         T c0 = (n1 * l2 - n2 * l1) * i2r, c1 = (n2 - n1) * i2r;
         h00 = c0 + c1 * h00; h01 = c1 * h01; h11 = c0 + c1 * h11;
       } else {
@@ -564,9 +591,9 @@ MPC_HD void backward_pass(const SolverConfig& cfg, const ProblemScalars<T>& p, c
     T Kg[2][6];
 #pragma unroll
     for (int jc = 0; jc < 6; ++jc) { Kg[0][jc] = T(0); Kg[1][jc] = T(0); }
-    if (s0 != 0 && ((s0 > 0) ? bx.sa_hi : bx.sa_lo)) Kg[0][3] = -T(1) / dt;          // keeps v+ on its bound
+    if (s0 != 0 && ((s0 > 0) ? bx.sa_hi : bx.sa_lo)) Kg[0][3] = -rcp_(dt);          // keeps v+ on its bound
     if (s1 != 0 && ((s1 > 0) ? bx.sd_hi : bx.sd_lo) && b3 > T(1e-12)) {              // keeps theta+ on its bound
-      T ib3 = T(1) / b3;
+      T ib3 = rcp_(b3);
       Kg[1][2] = -ib3;
       Kg[1][3] = -a34 * ib3;
     }
@@ -575,7 +602,7 @@ MPC_HD void backward_pass(const SolverConfig& cfg, const ProblemScalars<T>& p, c
     T E00 = max_(Quu00, T(0)), E01 = Quu01, E11 = max_(Quu11, T(0));
     if (s0 == 0 && s1 == 0) {
       E00 = f00; E01 = f01; E11 = f11;
-      T idet = T(1) / (h00 * h11 - h01 * h01);
+      T idet = rcp_(h00 * h11 - h01 * h01);
 #pragma unroll
       for (int jc = 0; jc < 6; ++jc) {
         Kg[0][jc] = -(h11 * Rz[0][jc] - h01 * Rz[1][jc]) * idet;
@@ -583,13 +610,13 @@ MPC_HD void backward_pass(const SolverConfig& cfg, const ProblemScalars<T>& p, c
       }
     } else if (s0 == 0) {
       E00 = max_(abs_(Quu00), T(cfg.reg_min)) + mu * (dt * dt + T(1));
-      T ih = T(1) / E00;
+      T ih = rcp_(E00);
       k0 = clamp_(-(Qu[0] + E01 * k1) * ih, bx.lo_a - a, bx.hi_a - a);
 #pragma unroll
       for (int jc = 0; jc < 6; ++jc) Kg[0][jc] = -(Rz[0][jc] + E01 * Kg[1][jc]) * ih;
     } else if (s1 == 0) {
       E11 = max_(abs_(Quu11), T(cfg.reg_min)) + mu * (b1 * b1 + b2 * b2 + b3 * b3 + T(1));
-      T ih = T(1) / E11;
+      T ih = rcp_(E11);
       k1 = clamp_(-(Qu[1] + E01 * k0) * ih, bx.lo_d - d, bx.hi_d - d);
 #pragma unroll
       for (int jc = 0; jc < 6; ++jc) Kg[1][jc] = -(Rz[1][jc] + E01 * Kg[0][jc]) * ih;
@@ -694,7 +721,14 @@ MPC_HD void solve_begin(const SolverConfig& cfg, const ProblemScalars<T>& p, con
   s.iter = 0; s.status = 0; s.trials = 0; s.done = false;
   T v0 = sl.X(0, 3), th0 = sl.X(0, 2);
   if (v0 < Lim<T>::v_min() || v0 > Lim<T>::v_max() || abs_(th0) > Lim<T>::th_max() * T(1.000001)) s.status |= kStatusInfeasibleStart;
-  s.J = rollout_nominal(cfg, p, ref, sl, (T*)nullptr);
+  // initial rollout = the commit pass under a zero policy (one code path for every rollout)
+  const T zero[2][6] = {{T(0), T(0), T(0), T(0), T(0), T(0)}, {T(0), T(0), T(0), T(0), T(0), T(0)}};
+  for (int k = 0; k < cfg.N; ++k) {
+    sl.store_gains(k, T(0), T(0), zero);
+    if (k > 0) { sl.X(k, 0) = T(0); sl.X(k, 1) = T(0); sl.X(k, 2) = T(0); sl.X(k, 3) = T(0); }   // defined nominal: 0 * stale shared memory could be NaN
+  }
+  T a1 = T(1), md;
+  forward_pass<T, 1, SL>(cfg, p, ref, sl, &a1, true, &s.J, &md);
   s.J_mark = s.J;
 }
 
@@ -722,8 +756,9 @@ MPC_HD void after_line_search(const SolverConfig& cfg, SolveState<T>& s, bool ac
   s.iter++;
   if (accepted) {
     s.J = Jn;
+    // a small step only proves stationarity when it is the un-damped Newton step
+    if (alpha == T(1) && s.mu == T(0) && maxdu < T(cfg.tol_step)) s.done = true;
     s.mu = s.mu > T(1e-3) ? s.mu * T(0.1) : T(0);
-    if (alpha == T(1) && maxdu < T(cfg.tol_step)) s.done = true;
   } else {
     s.mu = max_(s.mu * T(10), T(0.1));
     if (s.mu > T(1e9)) { s.status |= kStatusLineSearchFail; s.done = true; }
