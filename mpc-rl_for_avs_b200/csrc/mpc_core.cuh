@@ -75,7 +75,9 @@ MPC_HD void sincos_(double x, double* s, double* c) { *s = sin(x); *c = cos(x); 
 // every quantity they touch is either a search direction or carries 1e-5 relative tolerance
 MPC_HD float rcp_(float x) {
 #if defined(__CUDA_ARCH__)
-  return __fdividef(1.0f, x);
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));     // one MUFU.RCP, no range fix-up code
+  return r;
 #else
   return 1.0f / x;
 #endif
@@ -83,7 +85,9 @@ MPC_HD float rcp_(float x) {
 MPC_HD double rcp_(double x) { return 1.0 / x; }
 MPC_HD float rsqrt_(float x) {
 #if defined(__CUDA_ARCH__)
-  return rsqrtf(x);
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));   // one MUFU.RSQ
+  return r;
 #else
   return 1.0f / sqrtf(x);
 #endif
@@ -167,11 +171,13 @@ MPC_HD float bf_bits2f(uint32_t h) {
   memcpy(&f, &u, 4);
   return f;
 }
-template <typename T, bool kPack> struct Slots {
+// kStride > 0: the stride is a compile-time constant (= block size on the device), so every slot
+// address is base + immediate and no address arithmetic is issued; kStride = 0: run-time stride.
+template <typename T, bool kPack, int kStride = 0> struct Slots {
   T* base;
   int stride;
   int N, M;
-  MPC_HD T& at(int s) const { return base[(unsigned)s * (unsigned)stride]; }
+  MPC_HD T& at(int s) const { return base[(unsigned)s * (unsigned)(kStride > 0 ? kStride : stride)]; }
   static constexpr int kGainWords = kPack ? 7 : 14;
   // layout
   MPC_HD int oU() const { return 0; }                       // 2N
@@ -319,8 +325,8 @@ template <typename T> MPC_HD Box<T> control_box(T th, T v, T dt) {
   if (b.hi_a < b.lo_a) { b.hi_a = b.lo_a; }                 // v0 outside [0, 30]: keep a defined box
   const T gain = dt * v * T(1.0 / 2.5);                      // d theta+ / d sin beta
   const T reach = gain * sb_max<T>();
-  if (th + reach > Lim<T>::th_max()) { b.hi_d = delta_of_sinbeta((Lim<T>::th_max() - th) / gain); b.sd_hi = true; }
-  if (th - reach < -Lim<T>::th_max()) { b.lo_d = delta_of_sinbeta((-Lim<T>::th_max() - th) / gain); b.sd_lo = true; }
+  if (th + reach > Lim<T>::th_max()) { b.hi_d = delta_of_sinbeta((Lim<T>::th_max() - th) * rcp_(gain)); b.sd_hi = true; }
+  if (th - reach < -Lim<T>::th_max()) { b.lo_d = delta_of_sinbeta((-Lim<T>::th_max() - th) * rcp_(gain)); b.sd_lo = true; }
   if (b.hi_d < b.lo_d) { b.hi_d = b.lo_d; }
   return b;
 }
@@ -713,23 +719,25 @@ template <typename T> struct SolveState {
   bool done;
 };
 
+// Cold start (pure_mpc.py:244: zero controls).  The initial rollout is the commit pass under a zero
+// policy, so there is one rollout code path: solve_init, then forward_pass<T,1>(alpha = 1, commit),
+// then solve_init_finish with its objective.
 template <typename T, typename SL>
-MPC_HD void solve_begin(const SolverConfig& cfg, const ProblemScalars<T>& p, const RefTab<T>& ref,
-                        const SL& sl, SolveState<T>& s) {
-  for (int k = 0; k < cfg.N; ++k) { sl.U(k, 0) = T(0); sl.U(k, 1) = T(0); }   // cold start (pure_mpc.py:244)
+MPC_HD void solve_init(const SolverConfig& cfg, const SL& sl, SolveState<T>& s) {
+  const T zero[2][6] = {{T(0), T(0), T(0), T(0), T(0), T(0)}, {T(0), T(0), T(0), T(0), T(0), T(0)}};
+  for (int k = 0; k < cfg.N; ++k) {
+    sl.U(k, 0) = T(0); sl.U(k, 1) = T(0);
+    sl.store_gains(k, T(0), T(0), zero);
+    if (k > 0) { sl.X(k, 0) = T(0); sl.X(k, 1) = T(0); sl.X(k, 2) = T(0); sl.X(k, 3) = T(0); }   // 0 * stale memory could be NaN
+  }
   s.mu = T(0); s.hs = T(1);
   s.iter = 0; s.status = 0; s.trials = 0; s.done = false;
   T v0 = sl.X(0, 3), th0 = sl.X(0, 2);
   if (v0 < Lim<T>::v_min() || v0 > Lim<T>::v_max() || abs_(th0) > Lim<T>::th_max() * T(1.000001)) s.status |= kStatusInfeasibleStart;
-  // initial rollout = the commit pass under a zero policy (one code path for every rollout)
-  const T zero[2][6] = {{T(0), T(0), T(0), T(0), T(0), T(0)}, {T(0), T(0), T(0), T(0), T(0), T(0)}};
-  for (int k = 0; k < cfg.N; ++k) {
-    sl.store_gains(k, T(0), T(0), zero);
-    if (k > 0) { sl.X(k, 0) = T(0); sl.X(k, 1) = T(0); sl.X(k, 2) = T(0); sl.X(k, 3) = T(0); }   // defined nominal: 0 * stale shared memory could be NaN
-  }
-  T a1 = T(1), md;
-  forward_pass<T, 1, SL>(cfg, p, ref, sl, &a1, true, &s.J, &md);
-  s.J_mark = s.J;
+}
+template <typename T> MPC_HD void solve_init_finish(SolveState<T>& s, T J0) {
+  s.J = J0;
+  s.J_mark = J0;
 }
 
 template <typename T> struct Eps;
@@ -791,7 +799,12 @@ MPC_HD bool line_search_pass(const SolverConfig& cfg, const ProblemScalars<T>& p
 template <typename T, typename SL>
 MPC_HD void solve_one(const SolverConfig& cfg, const ProblemScalars<T>& p, const RefTab<T>& ref,
                       const SL& sl, SolveState<T>& s) {
-  solve_begin(cfg, p, ref, sl, s);
+  {
+    solve_init(cfg, sl, s);
+    T a1 = T(1), J0, md0;
+    forward_pass<T, 1, SL>(cfg, p, ref, sl, &a1, true, &J0, &md0);
+    solve_init_finish(s, J0);
+  }
   while (!s.done) {
     T d1, d2;
     backward_pass(cfg, p, ref, sl, s.mu, s.hs, &d1, &d2);

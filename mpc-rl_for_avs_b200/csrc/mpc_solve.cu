@@ -47,14 +47,17 @@ size_t solve_smem_bytes(int N, int M, int tpb) {
 __device__ __forceinline__ RefTab<float> stage_tables(float* smem) {
   double* xy = reinterpret_cast<double*>(smem);
   float* hsc = smem + kNRef * 2 * 2;
+#pragma unroll 1
   for (int i = threadIdx.x; i < kNRef * 2; i += blockDim.x) xy[i] = c_xy[i];
+#pragma unroll 1
   for (int i = threadIdx.x; i < kNRef * kRefStride; i += blockDim.x) hsc[i] = c_hsc[i];
   __syncthreads();
   return RefTab<float>{hsc, xy};
 }
 
+template <typename SL>
 __device__ __forceinline__ void load_problem(const MpcProblemBatch& b, int B, int i, const SolverConfig& cfg,
-                                             ProblemScalars<float>& p, const Slots<float, true>& sl) {
+                                             ProblemScalars<float>& p, const SL& sl) {
   p.ego_index = b.ego_index[i];
   int n = b.n_obs ? b.n_obs[i] : 0;
   p.n_obs = n < cfg.M ? n : cfg.M;
@@ -71,6 +74,7 @@ __device__ __forceinline__ void load_problem(const MpcProblemBatch& b, int B, in
   sl.X(0, 0) = 0.f; sl.X(0, 1) = 0.f;                       // positions are relative to the ego start
   sl.X(0, 2) = b.s0[(size_t)2 * B + i];
   sl.X(0, 3) = b.s0[(size_t)3 * B + i];
+#pragma unroll 1
   for (int m = 0; m < cfg.M; ++m) {
     if (b.obstacles) {
       sl.O(m, 0) = (float)((double)b.obstacles[((size_t)m * 4 + 0) * B + i] - p.x0);
@@ -83,66 +87,98 @@ __device__ __forceinline__ void load_problem(const MpcProblemBatch& b, int B, in
   }
 }
 
-__global__ void __launch_bounds__(192, 1)
+// One trip of the loop = [fetch] -> backward sweep -> line-search passes -> commit sweep -> bookkeeping,
+// each with exactly ONE call site so the kernel body stays near the instruction-cache size (the
+// first profile showed 2.3 stall cycles per issued instruction waiting for instructions).
+// A freshly fetched problem joins at the commit sweep (its first rollout is the commit under a zero
+// policy) and starts iterating on the next trip.
+template <int TPB>
+__global__ void __launch_bounds__(TPB, 1)
 k_solve(const SolverConfig cfg, const MpcProblemBatch batch, const MpcSolveOut out, const int B, int* __restrict__ work_counter) {
   extern __shared__ __align__(16) float smem[];
   const RefTab<float> ref = stage_tables(smem);
-  Slots<float, true> sl{smem + kTabFloats + threadIdx.x, (int)blockDim.x, cfg.N, cfg.M};
+  using SL = Slots<float, true, TPB>;
+  const SL sl{smem + kTabFloats + threadIdx.x, TPB, cfg.N, cfg.M};
   const unsigned full = 0xffffffffu;
 
   ProblemScalars<float> p;
   SolveState<float> s;
   int idx = -1;
-  bool active = false;
+  bool active = false, fresh = false, need_fetch = true;
 
-  auto fetch = [&]() {
-    idx = atomicAdd(work_counter, 1);
-    active = idx < B;
-    if (active) {
-      load_problem(batch, B, idx, cfg, p, sl);
-      solve_begin(cfg, p, ref, sl, s);
+  for (;;) {
+    if (need_fetch) {
+      need_fetch = false;
+      idx = atomicAdd(work_counter, 1);
+      active = idx < B;
+      if (active) {
+        load_problem(batch, B, idx, cfg, p, sl);
+        solve_init(cfg, sl, s);
+        fresh = true;
+      }
     }
-  };
-  fetch();
-
-  while (__any_sync(full, active)) {
-    float d1 = 0.f, d2 = 0.f;
-    if (active) backward_pass(cfg, p, ref, sl, s.mu, s.hs, &d1, &d2);
-    float alpha = 1.f, Jn = 0.f, md = 0.f;
+    if (!__any_sync(full, active)) break;
+    float d1 = 0.f, d2 = 0.f, alpha = 1.f, Jn = 0.f, md = 0.f;
     bool acc = false;
+    const bool run = active && !fresh;
+    if (run) backward_pass(cfg, p, ref, sl, s.mu, s.hs, &d1, &d2);
     for (int t = 0; t < kLineSearchPasses; ++t) {
-      const bool need = active && !acc;
+      const bool need = run && !acc;
       if (!__any_sync(full, need)) break;
       if (need) acc = line_search_pass(cfg, p, ref, sl, s, d1, d2, alpha);
     }
-    if (active && acc) forward_pass<float, 1, Slots<float, true>>(cfg, p, ref, sl, &alpha, true, &Jn, &md);
+    if (active && (fresh || acc)) forward_pass<float, 1, SL>(cfg, p, ref, sl, &alpha, true, &Jn, &md);
     if (active) {
-      after_line_search(cfg, s, acc, alpha, Jn, md);
-      if (s.done) {
-        if (!(s.J == s.J)) s.status |= kStatusNaN;
-        out.actions[2 * (size_t)idx] = sl.U(0, 0);
-        out.actions[2 * (size_t)idx + 1] = sl.U(0, 1);
-        if (out.status) out.status[idx] = s.status;
-        if (out.iters) out.iters[idx] = s.iter;
-        if (out.cost) out.cost[idx] = s.J;
-        if (out.U)
-          for (int k = 0; k < cfg.N; ++k) {
-            out.U[((size_t)idx * cfg.N + k) * 2] = sl.U(k, 0);
-            out.U[((size_t)idx * cfg.N + k) * 2 + 1] = sl.U(k, 1);
-          }
-        fetch();
+      if (fresh) {
+        solve_init_finish(s, Jn);
+        fresh = false;
+      } else {
+        after_line_search(cfg, s, acc, alpha, Jn, md);
+        if (s.done) {
+          if (!(s.J == s.J)) s.status |= kStatusNaN;
+          out.actions[2 * (size_t)idx] = sl.U(0, 0);
+          out.actions[2 * (size_t)idx + 1] = sl.U(0, 1);
+          if (out.status) out.status[idx] = s.status;
+          if (out.iters) out.iters[idx] = s.iter;
+          if (out.cost) out.cost[idx] = s.J;
+          if (out.U)
+#pragma unroll 1
+            for (int k = 0; k < cfg.N; ++k) {
+              out.U[((size_t)idx * cfg.N + k) * 2] = sl.U(k, 0);
+              out.U[((size_t)idx * cfg.N + k) * 2 + 1] = sl.U(k, 1);
+            }
+          active = false;
+          need_fetch = true;
+        }
       }
     }
   }
 }
 
-cudaError_t configure_solve_kernel(size_t smem_bytes) {
-  return cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+template <int TPB> static cudaError_t launch_solve_t(const SolveLaunch& s, cudaStream_t stream) {
+  // handles with different horizon / obstacle counts share the kernel: raise the opt-in limit as needed
+  static size_t configured = 0;
+  if (s.smem_bytes > configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_solve<TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.smem_bytes);
+    if (e != cudaSuccess) return e;
+    configured = s.smem_bytes;
+  }
+  k_solve<TPB><<<s.grid, TPB, s.smem_bytes, stream>>>(s.cfg, s.batch, s.out, s.B, s.work_counter);
+  return cudaGetLastError();
 }
 
+cudaError_t configure_solve_kernel(size_t) { return cudaSuccess; }
+
 cudaError_t launch_solve(const SolveLaunch& s, cudaStream_t stream) {
-  k_solve<<<s.grid, s.threads_per_block, s.smem_bytes, stream>>>(s.cfg, s.batch, s.out, s.B, s.work_counter);
-  return cudaGetLastError();
+  switch (s.threads_per_block) {
+    case 32: return launch_solve_t<32>(s, stream);
+    case 64: return launch_solve_t<64>(s, stream);
+    case 96: return launch_solve_t<96>(s, stream);
+    case 128: return launch_solve_t<128>(s, stream);
+    case 160: return launch_solve_t<160>(s, stream);
+    case 192: return launch_solve_t<192>(s, stream);
+    default: return cudaErrorInvalidConfiguration;
+  }
 }
 
 // ---- K1 parity entry: rollout + six cost components for given controls -----------------------
@@ -151,7 +187,7 @@ k_rollout_cost(const SolverConfig cfg, const MpcProblemBatch batch, const int B,
                float* __restrict__ X_out, float* __restrict__ cost6, float* __restrict__ total) {
   extern __shared__ __align__(16) float smem[];
   const RefTab<float> ref = stage_tables(smem);
-  Slots<float, true> sl{smem + kTabFloats + threadIdx.x, (int)blockDim.x, cfg.N, cfg.M};
+  const Slots<float, true> sl{smem + kTabFloats + threadIdx.x, (int)blockDim.x, cfg.N, cfg.M};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) {
     ProblemScalars<float> p;
     load_problem(batch, B, i, cfg, p, sl);
