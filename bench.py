@@ -241,15 +241,20 @@ def main() -> None:
     solve_ms = kt["solve_ms"]
     alg_flops = flops_per_solve(mean_iters) * B - 18.7e3 * M * B      # collision-check flops belong to k_prepare
     achieved = alg_flops / (solve_ms * 1e-3) / 1e12 if solve_ms > 0 else 0.0
+    hbm_bytes = (32 * M + 76) * B
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:  # noqa: BLE001
         pass
+    traffic = None
+    try:      # dram bytes read+written by k_solve per launch, from the committed `ncu --set full` capture of this command
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_k_solve_ncu_full.json")))["dram_traffic_bytes_per_launch"]
+    except Exception:  # noqa: BLE001
+        pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    hbm_bytes = (32 * M + 76) * B
     roofline = {"bound": "fp32", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
-                "traffic": None, "kernel": "k_solve", "kernel_ms": solve_ms, "prepare_kernel_ms": kt["prepare_ms"],
+                "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram__bytes_read+write; algorithmic %d)" % hbm_bytes, "kernel": "k_solve", "kernel_ms": solve_ms, "prepare_kernel_ms": kt["prepare_ms"],
                 "kernel_share_of_step": (solve_ms * kt["n_solve"]) / ms if ms else None,
                 "peak_source": "FP32 FMA micro-kernel measured in this run (mpc_fp32_peak); MEASURED_PEAKS.json holds only HBM/bf16",
                 "alg_flops_per_launch": alg_flops, "mean_iters": mean_iters,

@@ -715,7 +715,7 @@ enum : int {
 template <typename T> struct SolveState {
   T J, mu, hs;
   T J_mark;               // objective at the last progress checkpoint
-  int iter, status, trials;
+  int iter, status, trials, fails;
   bool done;
 };
 
@@ -731,7 +731,7 @@ MPC_HD void solve_init(const SolverConfig& cfg, const SL& sl, SolveState<T>& s) 
     if (k > 0) { sl.X(k, 0) = T(0); sl.X(k, 1) = T(0); sl.X(k, 2) = T(0); sl.X(k, 3) = T(0); }   // 0 * stale memory could be NaN
   }
   s.mu = T(0); s.hs = T(1);
-  s.iter = 0; s.status = 0; s.trials = 0; s.done = false;
+  s.iter = 0; s.status = 0; s.trials = 0; s.fails = 0; s.done = false;
   T v0 = sl.X(0, 3), th0 = sl.X(0, 2);
   if (v0 < Lim<T>::v_min() || v0 > Lim<T>::v_max() || abs_(th0) > Lim<T>::th_max() * T(1.000001)) s.status |= kStatusInfeasibleStart;
 }
@@ -768,7 +768,8 @@ MPC_HD void after_line_search(const SolverConfig& cfg, SolveState<T>& s, bool ac
     if (alpha == T(1) && s.mu == T(0) && maxdu < T(cfg.tol_step)) s.done = true;
     s.mu = s.mu > T(1e-3) ? s.mu * T(0.1) : T(0);
   } else {
-    s.mu = max_(s.mu * T(10), T(0.1));
+    s.fails++;
+    s.mu = max_(s.mu * T(30), T(3));
     if (s.mu > T(1e9)) { s.status |= kStatusLineSearchFail; s.done = true; }
   }
   if (!s.done && s.iter % kStallWindow == 0) {

@@ -86,7 +86,7 @@ static void run_solve(const SolverConfig& cfg, const double* ref, const HsBatch&
     actions[2 * i + 1] = float(sl.U(0, 1));
     status[i] = s.status;
     iters[i] = s.iter;
-    if (outer_out) outer_out[i] = s.trials;
+    if (outer_out) outer_out[i] = s.fails;
     cost[i] = float(s.J);
     if (U_out)
       for (int k = 0; k < cfg.N; ++k) { U_out[((size_t)i * cfg.N + k) * 2] = float(sl.U(k, 0)); U_out[((size_t)i * cfg.N + k) * 2 + 1] = float(sl.U(k, 1)); }
