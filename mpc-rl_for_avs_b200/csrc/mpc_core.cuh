@@ -165,6 +165,15 @@ MPC_HD uint32_t f2bf_bits(float f) {            // round-to-nearest-even float -
   memcpy(&u, &f, 4);
   return (u + 0x7FFFu + ((u >> 16) & 1u)) >> 16;
 }
+MPC_HD uint32_t pack_bf16x2(float lo, float hi) {   // word = hi:bf16 << 16 | lo:bf16
+#if defined(__CUDA_ARCH__)
+  uint32_t w;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(hi), "f"(lo));
+  return w;
+#else
+  return f2bf_bits(lo) | (f2bf_bits(hi) << 16);
+#endif
+}
 MPC_HD float bf_bits2f(uint32_t h) {
   uint32_t u = h << 16;
   float f;
@@ -193,10 +202,10 @@ template <typename T, bool kPack, int kStride = 0> struct Slots {
     if (kPack) {
 #pragma unroll
       for (int c = 0; c < 6; ++c) {
-        uint32_t w = f2bf_bits(float(Kg[0][c])) | (f2bf_bits(float(Kg[1][c])) << 16);
+        uint32_t w = pack_bf16x2(float(Kg[0][c]), float(Kg[1][c]));
         memcpy(&at(o + c), &w, 4);
       }
-      uint32_t w = f2bf_bits(float(k0)) | (f2bf_bits(float(k1)) << 16);
+      uint32_t w = pack_bf16x2(float(k0), float(k1));
       memcpy(&at(o + 6), &w, 4);
     } else {
 #pragma unroll
@@ -276,14 +285,16 @@ MPC_HD T stage_cost(const SolverConfig& cfg, const ProblemScalars<T>& p, const R
   if (k > 0) { T ea = a - ap, ed = d - dp; df = T(0.01) * (ea * ea + ed * ed); }
   T dist = T(0);
   if (cfg.w_distance != 0.f || comp) {
+    // c / (d + 1e-6)^2 with 1/(d + eps) = (1/d)(1 - eps/d + ...): one MUFU.RSQ per obstacle, the
+    // dropped (eps/d)^2 term is < 1e-12 relative for d > 1 mm
+    const T kf = T(k);
     for (int m = 0; m < p.n_obs; ++m) {
-      T ex = x - (sl.O(m, 0) + T(k) * sl.O(m, 2));
-      T ey = y - (sl.O(m, 1) + T(k) * sl.O(m, 3));
-      T d2 = ex * ex + ey * ey + T(1e-30);
-      T dd = d2 * rsqrt_(d2);
-      T ie = rcp_(dd + T(1e-6));
-      T c = dd < T(1) ? T(1000) : T(100);
-      dist += c * ie * ie;
+      T ex = (x - sl.O(m, 0)) - kf * sl.O(m, 2);
+      T ey = (y - sl.O(m, 1)) - kf * sl.O(m, 3);
+      T d2 = ex * ex + (ey * ey + T(1e-30));
+      T idd = rsqrt_(d2);
+      T c = d2 < T(1) ? T(1000) : T(100);
+      dist += c * (idd * idd) * (T(1) - T(2e-6) * idd);
     }
   }
   T col = p.is_collide ? T(3000) * v * v : T(0);
@@ -299,16 +310,17 @@ MPC_HD T stage_cost(const SolverConfig& cfg, const ProblemScalars<T>& p, const R
 // same set as a box on u_k whose edges depend on (theta_k, v_k).  The forward pass clamps to
 // that box exactly (every iterate is feasible); the backward pass treats a control sitting on a
 // state-dependent edge as the affine policy du = d(edge)/dx dx, i.e. the active-set SQP step.
+// The steering edge is kept in sin(beta) space (theta+ is affine in sin beta): the inverse map to a
+// steering angle (asinf) is only evaluated when a candidate control actually violates the edge.
 template <typename T> struct Box {
-  T lo_a, hi_a, lo_d, hi_d;
+  T lo_a, hi_a;         // acceleration bounds at this node
+  T sb_lo, sb_hi;       // bounds on sin(beta(delta)) at this node, within +-sin(beta(pi/3))
   bool sa_lo, sa_hi, sd_lo, sd_hi;   // edge comes from a state bound (not the constant limit)
 };
 template <typename T> MPC_HD T sb_max() { return T(0.6546536707079771); }   // sin beta(pi/3)
 MPC_HD float asin_(float x) { return asinf(x); }
 MPC_HD double asin_(double x) { return asin(x); }
-// inverse of sin beta(delta) = 0.5 sin d / sqrt(1 - 0.75 sin^2 d)
-// (rarely executed: only when a node sits within one step of the heading bound -- kept out of line
-// so that asinf is not inlined at every call site of control_box)
+// inverse of sin beta(delta) = 0.5 sin d / sqrt(1 - 0.75 sin^2 d); out of line: asinf is long and rare
 template <typename T> MPC_NOINLINE T delta_of_sinbeta(T sb) {
   sb = clamp_(sb, -sb_max<T>(), sb_max<T>());
   return asin_(sb * rsqrt_(T(0.25) + T(0.75) * sb * sb));
@@ -316,7 +328,7 @@ template <typename T> MPC_NOINLINE T delta_of_sinbeta(T sb) {
 template <typename T> MPC_HD Box<T> control_box(T th, T v, T dt) {
   Box<T> b;
   b.lo_a = -Lim<T>::a_max(); b.hi_a = Lim<T>::a_max();
-  b.lo_d = -Lim<T>::d_max(); b.hi_d = Lim<T>::d_max();
+  b.sb_lo = -sb_max<T>(); b.sb_hi = sb_max<T>();
   b.sa_lo = b.sa_hi = b.sd_lo = b.sd_hi = false;
   const T idt = rcp_(dt);
   T ha = (Lim<T>::v_max() - v) * idt, la = (Lim<T>::v_min() - v) * idt;
@@ -325,10 +337,20 @@ template <typename T> MPC_HD Box<T> control_box(T th, T v, T dt) {
   if (b.hi_a < b.lo_a) { b.hi_a = b.lo_a; }                 // v0 outside [0, 30]: keep a defined box
   const T gain = dt * v * T(1.0 / 2.5);                      // d theta+ / d sin beta
   const T reach = gain * sb_max<T>();
-  if (th + reach > Lim<T>::th_max()) { b.hi_d = delta_of_sinbeta((Lim<T>::th_max() - th) * rcp_(gain)); b.sd_hi = true; }
-  if (th - reach < -Lim<T>::th_max()) { b.lo_d = delta_of_sinbeta((-Lim<T>::th_max() - th) * rcp_(gain)); b.sd_lo = true; }
-  if (b.hi_d < b.lo_d) { b.hi_d = b.lo_d; }
+  if (th + reach > Lim<T>::th_max()) { b.sb_hi = (Lim<T>::th_max() - th) * rcp_(gain); b.sd_hi = true; }
+  if (th - reach < -Lim<T>::th_max()) { b.sb_lo = (-Lim<T>::th_max() - th) * rcp_(gain); b.sd_lo = true; }
+  if (b.sb_hi < b.sb_lo) { b.sb_hi = b.sb_lo; }
   return b;
+}
+// clamp a steering angle to the node's box; returns the steering terms of the clamped angle
+template <typename T> MPC_HD Steer<T> clamp_steer(const Box<T>& b, T& delta, bool second) {
+  delta = clamp_(delta, -Lim<T>::d_max(), Lim<T>::d_max());
+  Steer<T> st = steer_terms(delta, second);
+  if (st.sb > b.sb_hi || st.sb < b.sb_lo) {
+    delta = delta_of_sinbeta(clamp_(st.sb, b.sb_lo, b.sb_hi));
+    st = steer_terms(delta, second);
+  }
+  return st;
 }
 
 // ---- open-loop rollout of the stored controls; fills X, returns the objective ----------------
@@ -452,14 +474,14 @@ MPC_HD void backward_pass(const SolverConfig& cfg, const ProblemScalars<T>& p, c
       lvv = wv;
       if (cfg.w_distance != 0.f) {
         const T wd = T(cfg.w_distance);
+        const T kf = T(k);
         for (int m = 0; m < p.n_obs; ++m) {
-          T ex = x - (sl.O(m, 0) + T(k) * sl.O(m, 2));
-          T ey = y - (sl.O(m, 1) + T(k) * sl.O(m, 3));
-          T d2_ = ex * ex + ey * ey + T(1e-30);
+          T ex = (x - sl.O(m, 0)) - kf * sl.O(m, 2);
+          T ey = (y - sl.O(m, 1)) - kf * sl.O(m, 3);
+          T d2_ = ex * ex + (ey * ey + T(1e-30));
           T idd = rsqrt_(d2_);
-          T dd = d2_ * idd;
-          T cw = wd * (dd < T(1) ? T(1000) : T(100));
-          T ie = rcp_(dd + T(1e-6));
+          T cw = wd * (d2_ < T(1) ? T(1000) : T(100));
+          T ie = idd * (T(1) - T(1e-6) * idd);      // 1/(d + 1e-6) to first order in 1e-6/d
           T ie2 = ie * ie;
           T f1 = -T(2) * cw * ie2 * ie;          // phi'(d)
           T f2 = T(6) * cw * ie2 * ie2;          // phi''(d)
@@ -586,9 +608,16 @@ MPC_HD void backward_pass(const SolverConfig& cfg, const ProblemScalars<T>& p, c
     }
     // ---- box QP for the feed-forward on the (state-dependent) control box of this node
     const Box<T> bx = control_box(th, v, dt);
+    // steering edges for the QP in delta space, linearised at the nominal (exact when the nominal
+    // sits on the edge, which is the case that matters; the forward pass clamps exactly)
+    const T isl = rcp_(st.cb * st.g);                       // d delta / d sin beta
+    T hi_dd = Lim<T>::d_max() - d, lo_dd = -Lim<T>::d_max() - d;
+    bool sd_hi = false, sd_lo = false;
+    if (bx.sd_hi) { T e = max_((bx.sb_hi - st.sb) * isl, T(0)); if (e < hi_dd) { hi_dd = e; sd_hi = true; } }
+    if (bx.sd_lo) { T e = min_((bx.sb_lo - st.sb) * isl, T(0)); if (e > lo_dd) { lo_dd = e; sd_lo = true; } }
     T k0, k1;
     int s0, s1;
-    box_qp2(h00, h01, h11, Qu[0], Qu[1], bx.lo_a - a, bx.hi_a - a, bx.lo_d - d, bx.hi_d - d, &k0, &k1, &s0, &s1);
+    box_qp2(h00, h01, h11, Qu[0], Qu[1], bx.lo_a - a, bx.hi_a - a, lo_dd, hi_dd, &k0, &k1, &s0, &s1);
     // ---- gains: pinned coordinates follow their edge (constant edge: zero gain; edge that
     // comes from a node bound: d(edge)/dx), free coordinates minimise the model given those.
     // E = the control Hessian of the model that is actually minimised: the modified matrix on
@@ -598,7 +627,7 @@ MPC_HD void backward_pass(const SolverConfig& cfg, const ProblemScalars<T>& p, c
 #pragma unroll
     for (int jc = 0; jc < 6; ++jc) { Kg[0][jc] = T(0); Kg[1][jc] = T(0); }
     if (s0 != 0 && ((s0 > 0) ? bx.sa_hi : bx.sa_lo)) Kg[0][3] = -rcp_(dt);          // keeps v+ on its bound
-    if (s1 != 0 && ((s1 > 0) ? bx.sd_hi : bx.sd_lo) && b3 > T(1e-12)) {              // keeps theta+ on its bound
+    if (s1 != 0 && ((s1 > 0) ? sd_hi : sd_lo) && b3 > T(1e-12)) {              // keeps theta+ on its bound
       T ib3 = rcp_(b3);
       Kg[1][2] = -ib3;
       Kg[1][3] = -a34 * ib3;
@@ -623,13 +652,13 @@ MPC_HD void backward_pass(const SolverConfig& cfg, const ProblemScalars<T>& p, c
     } else if (s1 == 0) {
       E11 = max_(abs_(Quu11), T(cfg.reg_min)) + mu * (b1 * b1 + b2 * b2 + b3 * b3 + T(1));
       T ih = rcp_(E11);
-      k1 = clamp_(-(Qu[1] + E01 * k0) * ih, bx.lo_d - d, bx.hi_d - d);
+      k1 = clamp_(-(Qu[1] + E01 * k0) * ih, lo_dd, hi_dd);
 #pragma unroll
       for (int jc = 0; jc < 6; ++jc) Kg[1][jc] = -(Rz[1][jc] + E01 * Kg[0][jc]) * ih;
     }
 #if defined(MPC_TRACE2) && !defined(__CUDA_ARCH__)
     printf("  k %d Quu %.4g %.4g %.4g Hdd %.4g Qu %.4g %.4g kff %.4g %.4g side %d %d box d [%.4g %.4g] sd %d %d P22 %.4g P33 %.4g p %.3g %.3g %.3g %.3g\n", k, (double)Quu00, (double)Quu01, (double)Quu11, (double)Hdd,
-           (double)Qu[0], (double)Qu[1], (double)k0, (double)k1, s0, s1, (double)bx.lo_d, (double)bx.hi_d, (int)bx.sd_lo, (int)bx.sd_hi, (double)P[sym6(2,2)], (double)P[sym6(3,3)], (double)pv[0], (double)pv[1], (double)pv[2], (double)pv[3]);
+           (double)Qu[0], (double)Qu[1], (double)k0, (double)k1, s0, s1, (double)lo_dd, (double)hi_dd, (int)sd_lo, (int)sd_hi, (double)P[sym6(2,2)], (double)P[sym6(3,3)], (double)pv[0], (double)pv[1], (double)pv[2], (double)pv[3]);
 #endif
     sl.store_gains(k, k0, k1, Kg);
     // ---- predicted change and value update
@@ -685,7 +714,8 @@ MPC_HD void forward_pass(const SolverConfig& cfg, const ProblemScalars<T>& p, co
       const T dd = alpha[a] * f1 + Kr[6] * ex + Kr[7] * ey + Kr[8] * eth + Kr[9] * ev + Kr[10] * dap[a] + Kr[11] * ddp[a];
       const Box<T> bx = control_box(th[a], v[a], dt);
       const T ac = clamp_(ua + da, bx.lo_a, bx.hi_a);
-      const T dc = clamp_(ud + dd, bx.lo_d, bx.hi_d);
+      T dc = ud + dd;
+      const Steer<T> st = clamp_steer(bx, dc, false);
       dap[a] = ac - ua; ddp[a] = dc - ud;
       maxdu[a] = max_(maxdu[a], max_(abs_(dap[a]), abs_(ddp[a])));
       J[a] += stage_cost(cfg, p, ref, sl, k, x[a], y[a], th[a], v[a], ac, dc, ap[a], dp[a], (T*)nullptr);
@@ -693,7 +723,6 @@ MPC_HD void forward_pass(const SolverConfig& cfg, const ProblemScalars<T>& p, co
         sl.X(k, 0) = x[a]; sl.X(k, 1) = y[a]; sl.X(k, 2) = th[a]; sl.X(k, 3) = v[a];
         sl.U(k, 0) = ac; sl.U(k, 1) = dc;
       }
-      Steer<T> st = steer_terms(dc, false);
       euler_step(x[a], y[a], th[a], v[a], ac, st, dt);
       ap[a] = ac; dp[a] = dc;
     }
