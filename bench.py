@@ -79,7 +79,7 @@ def run_reference(args) -> None:
     import numpy as np
     import mpc_rl_for_avs_b200 as pkg
     cores = os.cpu_count() or 1
-    per_step = args.ref_problems if args.ref_problems > 0 else 4 * cores
+    per_step = args.ref_problems if args.ref_problems > 0 else 24 * cores
     obs, rs, has = pkg.make_scenarios(per_step * (args.steps + args.warmup), M, seed=1234)
     obs, rs, has = obs.numpy(), rs.numpy(), has.numpy()
     items = [(obs[i], (rs[i] if has[i] else None)) for i in range(obs.shape[0])]
