@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmpcb200.so")
+LIB_PATH = os.path.join(_HERE, os.environ.get("MPC_LIB_NAME", "libmpcb200.so"))   # override only for A/B experiment builds
 
 ABI_VERSION = 1
 MAX_OBSTACLES = 16

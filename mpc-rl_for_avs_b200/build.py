@@ -14,7 +14,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libmpcb200.so")
+LIB = os.path.join(HERE, os.environ.get("MPC_LIB_NAME", "libmpcb200.so"))      # MPC_LIB_NAME / MPC_BUILD_DEFS: A/B experiment builds only
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
           "--expt-relaxed-constexpr"]
@@ -40,12 +40,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
     nvcc = _nvcc()
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build", os.path.basename(LIB))
     os.makedirs(objdir, exist_ok=True)
     objs = []
     for src, extra in UNITS:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc, *ARCH, *COMMON, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *ARCH, *COMMON, *extra, *os.environ.get("MPC_BUILD_DEFS", "").split(), "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas")
             cmd.insert(2, "-v")

@@ -105,7 +105,7 @@ MPC_API int mpc_create(const MpcConfig* cfg, int device, int max_batch, MpcHandl
   s.max_iter = cfg->max_iter > 0 ? cfg->max_iter : 60;
   s.tol_step = cfg->tol_step > 0.f ? cfg->tol_step : 1e-4f;
   s.reg_min = cfg->reg_min > 0.f ? cfg->reg_min : 1e-2f;
-  s.stall_tol = 1e-5f;
+  s.stall_tol = 1e-4f;
 
 #define CKC(call)                                                                        \
   do {                                                                                   \

@@ -32,6 +32,15 @@
 #define MPC_HD inline
 #endif
 
+// obstacle loops: the per-obstacle chain (LDS -> FMA -> MUFU.RSQ -> FMA) is long and serial; unrolling
+// overlaps several obstacles' chains (the kernel is latency bound)
+#ifndef MPC_OBS_UNROLL
+#define MPC_OBS_UNROLL 4
+#endif
+#define MPC_STR2(x) #x
+#define MPC_STR(x) MPC_STR2(x)
+#define MPC_PRAGMA_UNROLL_OBS _Pragma(MPC_STR(unroll MPC_OBS_UNROLL))
+
 namespace mpcb {
 
 constexpr int kNRef = 85;          // agents/base_agent.py:127-152 (40 + 20 + 25 rows)
@@ -288,6 +297,7 @@ MPC_HD T stage_cost(const SolverConfig& cfg, const ProblemScalars<T>& p, const R
     // c / (d + 1e-6)^2 with 1/(d + eps) = (1/d)(1 - eps/d + ...): one MUFU.RSQ per obstacle, the
     // dropped (eps/d)^2 term is < 1e-12 relative for d > 1 mm
     const T kf = T(k);
+MPC_PRAGMA_UNROLL_OBS
     for (int m = 0; m < p.n_obs; ++m) {
       T ex = (x - sl.O(m, 0)) - kf * sl.O(m, 2);
       T ey = (y - sl.O(m, 1)) - kf * sl.O(m, 3);
@@ -475,6 +485,7 @@ MPC_HD void backward_pass(const SolverConfig& cfg, const ProblemScalars<T>& p, c
       if (cfg.w_distance != 0.f) {
         const T wd = T(cfg.w_distance);
         const T kf = T(k);
+MPC_PRAGMA_UNROLL_OBS
         for (int m = 0; m < p.n_obs; ++m) {
           T ex = (x - sl.O(m, 0)) - kf * sl.O(m, 2);
           T ey = (y - sl.O(m, 1)) - kf * sl.O(m, 3);

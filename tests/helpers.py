@@ -101,7 +101,7 @@ class HsBatch(C.Structure):
                 ("is_collide", _P(C.c_ubyte)), ("n_obs", _P(C.c_int)), ("obstacles", _P(C.c_float))]
 
 
-def hs_config(N=20, M=8, dt=0.1, w_distance=0.0, w_collision=0.0, literal=0, max_iter=60, tol_step=1e-4, reg_min=1e-2, stall_tol=1e-5):
+def hs_config(N=20, M=8, dt=0.1, w_distance=0.0, w_collision=0.0, literal=0, max_iter=60, tol_step=1e-4, reg_min=1e-2, stall_tol=1e-4):
     return HsConfig(N=N, M=M, dt=dt, w_distance=w_distance, w_collision=w_collision, literal_no_collision=literal,
                     max_iter=max_iter, tol_step=tol_step, reg_min=reg_min, stall_tol=stall_tol)
 
