@@ -290,7 +290,7 @@ def cpu_baseline(seconds: float):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import mpc_rl_for_avs_b200 as pkg
     cores = os.cpu_count() or 1
-    n = max(cores * 2, int(seconds * cores / 0.25))
+    n = max(cores * 2, int(seconds * cores / 0.08))      # ~0.08 s per oracle predict per core
     obs, rs, has = pkg.make_scenarios(n, M, seed=1234)
     obs, rs, has = obs.numpy(), rs.numpy(), has.numpy()
     items = [(obs[i], (rs[i] if has[i] else None)) for i in range(n)]
