@@ -337,3 +337,78 @@ def test_edge_cases():
     o3[:, 0, 3], o3[:, 0, 4] = 0.0, -35.0
     a3 = agent.predict_batch(o3.cuda())
     assert torch.isfinite(a3).all() and ((agent.status[:33] & 8) != 0).all()
+
+
+# --------------------------------------------------------------------------------------- other configurations
+def test_shipped_config_horizon16_ten_vehicles():
+    """The reference ships horizon 16 and vehicles_count 10 (config/cfg.yaml:90, :2): nine other vehicles take
+    the 16-lanes-per-environment prepare kernel and a different shared-memory layout."""
+    pkg = _pkg()
+    B, M, N = 48, 9, 16
+    cfg = dict(CFG, horizon=N)
+    obs, rs, has = pkg.make_scenarios(B, M, seed=31)
+    agent = pkg.BatchedPureMPC(cfg, vehicles_count=M + 1, max_batch=B, collision_check=True, weight_distance=10.0)
+    rsn = torch.where(has.reshape(-1, 1), rs, torch.full_like(rs, float("nan"))).cuda()
+    actions, U = agent.predict_batch(obs.cuda(), ref_speed=rsn, return_controls=True)
+    torch.cuda.synchronize()
+    U = U.cpu().numpy()
+    assert U.shape == (B, N, 2)
+    probs, _ = helpers.problems_from_obs(obs.numpy(), rs.numpy(), has.numpy(), w_distance=10.0, collision_check=True, N=N)
+    deg = np.array([orc.detect_collisions(orc.parse_obs(o, M + 1).ego, orc.parse_obs(o, M + 1).others).degenerate for o in obs.numpy()])
+    nd = ~deg
+    assert np.array_equal(agent.is_collide[:B].cpu().numpy().astype(bool)[nd], np.array([p.is_collide for p in probs])[nd])
+    assert np.array_equal(agent.ego_index[:B].cpu().numpy(), np.array([p.ego_index for p in probs]))
+    st = agent.status[:B].cpu().numpy()
+    assert (st == 0).mean() >= 0.8
+    for i in np.nonzero((st == 0) & nd)[0][:24]:
+        ok, du0, gain = helpers.oracle_warm_confirms(probs[i], U[i])
+        assert ok, (i, du0, gain)
+        c64 = orc.objective(U[i].astype(np.float64), probs[i])
+        near, tol = helpers.distance_conditioning(probs[i], U[i])
+        if not near:
+            assert abs(agent.cost[i].item() - c64) <= 2e-5 * max(1.0, abs(c64)) + 10 * tol
+
+
+def test_rl_weights_and_literal_no_collision_mode():
+    pkg = _pkg()
+    B, M = 64, 8
+    obs, _, _ = pkg.make_scenarios(B, M, seed=41)
+    # v1 of the RL agents: weights_from_RL (speed, control, input_diff) per environment (agents/pure_mpc.py:96-104)
+    rng = np.random.default_rng(0)
+    w = rng.uniform(0.2, 3.0, (B, 3)).astype(np.float32)
+    agent = pkg.BatchedPureMPC(CFG, vehicles_count=M + 1, max_batch=B, collision_check=False)
+    actions, U = agent.predict_batch(obs.cuda(), weights=torch.from_numpy(w).cuda(), return_controls=True)
+    torch.cuda.synchronize()
+    U = U.cpu().numpy()
+    st = agent.status[:B].cpu().numpy()
+    n = 0
+    for i in np.nonzero(st == 0)[0][:20]:
+        ag = orc.OraclePureMPCAgent(horizon=20, vehicles_count=M + 1, collision_check=False)
+        p = ag.build_problem(orc.parse_obs(obs[i].numpy(), M + 1), weights_from_RL=w[i:i + 1])
+        assert (p.w_speed, p.w_control, p.w_input_diff) == tuple(float(x) for x in w[i])
+        ok, du0, gain = helpers.oracle_warm_confirms(p, U[i])
+        assert ok, (i, du0, gain)
+        n += 1
+    assert n >= 10
+    # literal objective of pure_mpc_no_collision.py:146-151: control effort only -> u = 0 is optimal (quirk Q3)
+    lit = pkg.BatchedPureMPC(CFG, vehicles_count=M + 1, max_batch=B, collision_check=False, literal_no_collision=True)
+    a = lit.predict_batch(obs.cuda())
+    assert float(a.abs().max()) <= 1e-6 and (lit.status[:B] == 0).all() and float(lit.cost[:B].abs().max()) <= 1e-9
+
+
+def test_config2_4096_no_collision_batch():
+    """BASELINE config 2: 4096 problems, H=20, no collision logic, tracking objective."""
+    pkg = _pkg()
+    B = 4096
+    obs, rs, has = pkg.make_scenarios(B, 0, seed=51)
+    agent = pkg.BatchedPureMPC(CFG, vehicles_count=1, max_batch=B, collision_check=False)
+    rsn = torch.where(has.reshape(-1, 1), rs, torch.full_like(rs, float("nan"))).cuda()
+    a, U = agent.predict_batch(obs.cuda(), ref_speed=rsn, return_controls=True)
+    torch.cuda.synchronize()
+    st = agent.status[:B].cpu().numpy()
+    assert (st == 0).mean() >= 0.85 and torch.isfinite(a).all()
+    probs, _ = helpers.problems_from_obs(obs.numpy()[:64], rs.numpy()[:64], has.numpy()[:64])
+    U = U.cpu().numpy()
+    for i in np.nonzero(st[:64] == 0)[0][:24]:
+        ok, du0, gain = helpers.oracle_warm_confirms(probs[i], U[i])
+        assert ok, (i, du0, gain)

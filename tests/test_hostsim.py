@@ -99,3 +99,17 @@ def test_survey_known_answers(hostsim):
     for i, (_, f, u0) in enumerate(cases):
         assert np.max(np.abs(r["actions"][i] - np.array(u0))) <= 1e-3
         assert abs(r["cost"][i] - f) <= 1e-4 * f
+
+
+def test_horizon16_solver_logic(hostsim):
+    """Shipped horizon (config/cfg.yaml:90) through the same device functions."""
+    import mpc_rl_for_avs_b200 as pkg
+    B, M, N = 32, 9, 16
+    obs, rs, has = pkg.make_scenarios(B, M, seed=31)
+    probs, _ = helpers.problems_from_obs(obs.numpy(), rs.numpy(), has.numpy(), w_distance=10.0, collision_check=True, N=N)
+    r = helpers.hostsim_solve(hostsim, helpers.batch_from_problems(probs, M), helpers.hs_config(N=N, M=M, w_distance=10.0))
+    conv = r["status"] == 0
+    assert conv.mean() >= 0.8
+    for i in np.nonzero(conv)[0][:12]:
+        ok, du0, gain = helpers.oracle_warm_confirms(probs[i], r["U"][i])
+        assert ok, (i, du0, gain)
