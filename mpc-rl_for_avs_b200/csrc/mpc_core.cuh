@@ -700,10 +700,11 @@ MPC_PRAGMA_UNROLL_OBS
 // node's control box, for NA step lengths AT ONCE (independent dependency chains: the kernel is
 // latency bound, so the second candidate is almost free and the gains are loaded once).
 // commit (NA == 1 only): overwrite (X, U) in place with the new trajectory.
+// with_cost = false skips the objective (the commit of an accepted trial already knows it).
 // J[a] = objective, maxdu[a] = max |u_new - u_old| over the horizon.
 template <typename T, int NA, typename SL>
 MPC_HD void forward_pass(const SolverConfig& cfg, const ProblemScalars<T>& p, const RefTab<T>& ref,
-                         const SL& sl, const T* alpha, bool commit, T* J, T* maxdu) {
+                         const SL& sl, const T* alpha, bool commit, bool with_cost, T* J, T* maxdu) {
   const int N = cfg.N;
   const T dt = T(cfg.dt);
   T x[NA], y[NA], th[NA], v[NA], ap[NA], dp[NA], dap[NA], ddp[NA];
@@ -729,7 +730,7 @@ MPC_HD void forward_pass(const SolverConfig& cfg, const ProblemScalars<T>& p, co
       const Steer<T> st = clamp_steer(bx, dc, false);
       dap[a] = ac - ua; ddp[a] = dc - ud;
       maxdu[a] = max_(maxdu[a], max_(abs_(dap[a]), abs_(ddp[a])));
-      J[a] += stage_cost(cfg, p, ref, sl, k, x[a], y[a], th[a], v[a], ac, dc, ap[a], dp[a], (T*)nullptr);
+      if (with_cost) J[a] += stage_cost(cfg, p, ref, sl, k, x[a], y[a], th[a], v[a], ac, dc, ap[a], dp[a], (T*)nullptr);
       if (NA == 1 && commit) {
         sl.X(k, 0) = x[a]; sl.X(k, 1) = y[a]; sl.X(k, 2) = th[a]; sl.X(k, 3) = v[a];
         sl.U(k, 0) = ac; sl.U(k, 1) = dc;
@@ -822,15 +823,15 @@ MPC_HD void after_line_search(const SolverConfig& cfg, SolveState<T>& s, bool ac
 }
 
 // one line-search pass: tries alpha and alpha/2 together.  On success `alpha` holds the accepted step
-// length; otherwise it is divided by 4 for the next pass.
+// length and (Jacc, mdacc) its objective and step size; otherwise alpha is divided by 4 for the next pass.
 template <typename T, typename SL>
 MPC_HD bool line_search_pass(const SolverConfig& cfg, const ProblemScalars<T>& p, const RefTab<T>& ref,
-                             const SL& sl, SolveState<T>& s, T d1, T d2, T& alpha) {
+                             const SL& sl, SolveState<T>& s, T d1, T d2, T& alpha, T& Jacc, T& mdacc) {
   T al[2] = {alpha, alpha * T(0.5)}, Jt[2], mt[2];
-  forward_pass<T, 2, SL>(cfg, p, ref, sl, al, false, Jt, mt);
+  forward_pass<T, 2, SL>(cfg, p, ref, sl, al, false, true, Jt, mt);
   s.trials += 2;
-  if (accept_step(s.J, Jt[0], al[0] * d1 + al[0] * al[0] * d2)) { alpha = al[0]; return true; }
-  if (accept_step(s.J, Jt[1], al[1] * d1 + al[1] * al[1] * d2)) { alpha = al[1]; return true; }
+  if (accept_step(s.J, Jt[0], al[0] * d1 + al[0] * al[0] * d2)) { alpha = al[0]; Jacc = Jt[0]; mdacc = mt[0]; return true; }
+  if (accept_step(s.J, Jt[1], al[1] * d1 + al[1] * al[1] * d2)) { alpha = al[1]; Jacc = Jt[1]; mdacc = mt[1]; return true; }
   alpha = alpha * T(0.25);
   return false;
 }
@@ -843,7 +844,7 @@ MPC_HD void solve_one(const SolverConfig& cfg, const ProblemScalars<T>& p, const
   {
     solve_init(cfg, sl, s);
     T a1 = T(1), J0, md0;
-    forward_pass<T, 1, SL>(cfg, p, ref, sl, &a1, true, &J0, &md0);
+    forward_pass<T, 1, SL>(cfg, p, ref, sl, &a1, true, true, &J0, &md0);
     solve_init_finish(s, J0);
   }
   while (!s.done) {
@@ -852,9 +853,9 @@ MPC_HD void solve_one(const SolverConfig& cfg, const ProblemScalars<T>& p, const
     T alpha = T(1), Jn = T(0), md = T(0);
     bool acc = false;
     for (int t = 0; t < kLineSearchPasses && !acc; ++t) {
-      acc = line_search_pass(cfg, p, ref, sl, s, d1, d2, alpha);
+      acc = line_search_pass(cfg, p, ref, sl, s, d1, d2, alpha, Jn, md);
     }
-    if (acc) forward_pass<T, 1, SL>(cfg, p, ref, sl, &alpha, true, &Jn, &md);
+    if (acc) { T Jc, mdc; forward_pass<T, 1, SL>(cfg, p, ref, sl, &alpha, true, false, &Jc, &mdc); }
 #if defined(MPC_TRACE) && !defined(__CUDA_ARCH__)
     printf("it %d J %.9g d1 %.4g d2 %.4g alpha %.4g acc %d Jn %.9g maxdu %.3g mu %.3g hs %g u0 %.6f %.6f\n", s.iter, (double)s.J,
            (double)d1, (double)d2, (double)alpha, (int)acc, (double)Jn, (double)md, (double)s.mu, (double)s.hs, (double)sl.U(0, 0), (double)sl.U(0, 1));

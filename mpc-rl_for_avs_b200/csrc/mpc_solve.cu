@@ -125,9 +125,13 @@ k_solve(const SolverConfig cfg, const MpcProblemBatch batch, const MpcSolveOut o
     for (int t = 0; t < kLineSearchPasses; ++t) {
       const bool need = run && !acc;
       if (!__any_sync(full, need)) break;
-      if (need) acc = line_search_pass(cfg, p, ref, sl, s, d1, d2, alpha);
+      if (need) acc = line_search_pass(cfg, p, ref, sl, s, d1, d2, alpha, Jn, md);
     }
-    if (active && (fresh || acc)) forward_pass<float, 1, SL>(cfg, p, ref, sl, &alpha, true, &Jn, &md);
+    if (active && (fresh || acc)) {      // commit sweep; only a fresh problem still needs its objective
+      float Jc, mdc;
+      forward_pass<float, 1, SL>(cfg, p, ref, sl, &alpha, true, fresh, &Jc, &mdc);
+      if (fresh) Jn = Jc;
+    }
     if (active) {
       if (fresh) {
         solve_init_finish(s, Jn);
