@@ -151,7 +151,7 @@ def main() -> None:
     nsteps = args.warmup + args.steps
     # distinct batches per step; inputs live in HBM before the timed region (value) and in pinned host
     # memory (e2e).  Distinct data per step: nothing is cached between steps.
-    n_unique = min(nsteps, 6)
+    n_unique = min(nsteps, 8)       # 8 x 19.4 MB of inputs > 126 MB L2
     batches = []
     for s in range(n_unique):
         obs, rs, has = pkg.make_scenarios(B, M, seed=1234 + rank + 1000 * s)
@@ -203,20 +203,18 @@ def main() -> None:
     ms = float(t.item())
     value = total * args.steps / (ms * 1e-3)
 
-    # ---- e2e: host buffers in, host result out, through the reference-facing call ------------------
+    # ---- e2e: HOST buffers through the C-ABI host entry point (mpc_predict_host): pinned numpy in,
+    # numpy out, H2D of obs/ref_speed/reset mask and D2H of actions/status/is_collide inside the call
+    host_np = [(o.numpy(), r.numpy()) for o, r in host_batches]          # views of the pinned buffers
+    reset_all = torch.ones(B, dtype=torch.uint8).pin_memory().numpy()
     h2d = d2h = 0
-    acts_host = torch.empty(B, 2, dtype=torch.float32).pin_memory()
-    stat_host = torch.empty(B, dtype=torch.int32).pin_memory()
 
     def e2e_step(i):
-        o, r = host_batches[i % n_unique]
-        od, rd = o.to(dev, non_blocking=True), r.to(dev, non_blocking=True)
-        agent.reset()
-        a = agent.predict_batch(od, ref_speed=rd)
-        acts_host.copy_(a, non_blocking=True)
-        stat_host.copy_(agent.status[:B], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return o.numel() * 4 + r.numel() * 4, acts_host.numel() * 4 + stat_host.numel() * 4
+        o, r = host_np[i % n_unique]
+        acts, stat, iscol, up, down = agent.predict_host(o, r, reset_mask=reset_all)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, torch.from_numpy(acts).to(dev))
+        return up, down
 
     for i in range(3):
         e2e_step(i)
@@ -271,7 +269,7 @@ def main() -> None:
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "horizon": H, "obstacles": M,
-                       "l2": "inputs of consecutive steps are different buffers (6 distinct batches, 19 MB each); "
+                       "l2": "inputs rotate over 8 distinct batches (8 x 19.4 MB > the 126 MB L2); "
                              "the per-step working set is on-chip, HBM traffic is the compulsory ~0.3 KB/problem",
                        "parallelism": f"env-sharded x{world}" + (", all_gather(actions)" if world > 1 else "")},
             "solver": {"mean_iters": mean_iters, "p50_iters": float(it.median()), "p99_iters": float(torch.quantile(it, 0.99)),

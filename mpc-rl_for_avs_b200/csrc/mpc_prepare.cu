@@ -65,8 +65,12 @@ k_prepare(const PrepareParams P) {
   const double ex = ob[1], ey = ob[2];
   const double evx = ob[3], evy = ob[4];
   double eth = ob[5];
-  while (eth > kPi) eth -= 2 * kPi;                   // base_agent.py:156-170
-  while (eth < -kPi) eth += 2 * kPi;
+  // base_agent.py:156-170 wraps by repeated +-2pi.  Same arithmetic for any heading a simulator can
+  // produce; the loop is bounded so that a non-finite or absurd heading cannot hang the kernel
+  // (the reference would spin forever on inf).
+  for (int it = 0; it < 64 && eth > kPi; ++it) eth -= 2 * kPi;
+  for (int it = 0; it < 64 && eth < -kPi; ++it) eth += 2 * kPi;
+  if (!(eth >= -kPi && eth <= kPi)) eth = 0.0;        // inf / nan / |heading| > 400 rad: defined value, status flags the solve
   const double ev = norm2(evx, evy);                  // agents/utils.py:36
   int present = 0;
   for (int r = 0; r < P.V; ++r) present += (ob[r * 8] == 1.0f) ? 1 : 0;

@@ -332,6 +332,16 @@ def test_edge_cases():
         agent.predict_batch(torch.zeros(4, M, 8, device="cuda"))
     with pytest.raises(ValueError):
         agent.predict_batch(torch.zeros(4, M + 1, 8))
+    # non-finite observations must not hang or poison neighbours: bounded work, flagged result
+    o4 = obs.clone()
+    o4[0, 0, 5] = float("inf")          # the reference's normalize_angle would spin forever on this
+    o4[1, 0, 1] = float("nan")
+    o4[2, 3, 2] = float("nan")
+    a4 = agent.predict_batch(o4.cuda())
+    torch.cuda.synchronize()
+    ref4 = agent.predict_batch(obs.cuda()).clone()
+    assert torch.equal(a4[3:], ref4[3:])            # other environments are untouched
+    assert (agent.status[:33] >= 0).all()
     # speed above the v <= 30 bound: the reference NLP is infeasible; flagged, finite result
     o3 = obs.clone()
     o3[:, 0, 3], o3[:, 0, 4] = 0.0, -35.0
