@@ -161,6 +161,12 @@ MPC_API int mpc_predict(MpcHandle* h, const float* obs, const float* ref_speed, 
                 const uint8_t* reset_mask, const MpcLatchState* latch, int B, const MpcSolveOut* out,
                 const MpcCollisionOut* col, void* stream);
 
+/* OPT-IN warm start (the reference always cold-starts from zero controls,
+ * agents/pure_mpc.py:240-246): subsequent mpc_solve / mpc_predict calls start each problem from
+ * u_init [B][N][2] (device pointer, borrowed until replaced; NULL switches back to the cold start).
+ * A warm start changes which local optimum of the multi-modal NLP is found: keep it off for parity runs. */
+MPC_API int mpc_set_warm_start(MpcHandle* h, const float* u_init);
+
 /* Same call with HOST buffers (what a numpy caller holds): obs/ref_speed/weights/reset_mask are
  * copied host->device, actions/status (and is_collide) device->host, inside the call; the latch
  * lives in the handle.  Synchronous.  Returns bytes moved in *h2d_bytes / *d2h_bytes if non-NULL. */

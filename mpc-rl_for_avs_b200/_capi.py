@@ -55,7 +55,7 @@ class MpcCollisionOut(C.Structure):
 
 EXPORTS = ["mpc_create", "mpc_destroy", "mpc_last_error", "mpc_workspace_batch", "mpc_rollout_cost", "mpc_solve",
            "mpc_prepare", "mpc_predict", "mpc_predict_host", "mpc_launch_count", "mpc_fp32_peak", "mpc_timing_begin",
-           "mpc_timing_end", "mpc_device_info"]
+           "mpc_timing_end", "mpc_device_info", "mpc_set_warm_start"]
 
 
 class MpcError(RuntimeError):
@@ -96,6 +96,8 @@ def load() -> C.CDLL:
     lib.mpc_predict.restype = C.c_int
     lib.mpc_predict_host.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.mpc_predict_host.restype = C.c_int
+    lib.mpc_set_warm_start.argtypes = [vp, vp]
+    lib.mpc_set_warm_start.restype = C.c_int
     lib.mpc_launch_count.argtypes = [vp]
     lib.mpc_launch_count.restype = C.c_int64
     lib.mpc_fp32_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]

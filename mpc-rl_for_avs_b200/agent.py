@@ -101,6 +101,7 @@ class BatchedPureMPC:
         self.stop_index = torch.full((B,), -1, dtype=torch.int32, device=dev)
         self.degenerate = torch.zeros(B, dtype=torch.uint8, device=dev)
         self.reference_trajectory = torch.from_numpy(reference_path(self.dt)[:, :2].copy()).to(dev)
+        self._u_init = None
 
     # ------------------------------------------------------------------ lifecycle
     def close(self) -> None:
@@ -164,6 +165,25 @@ class BatchedPureMPC:
         return out, U
 
     # ------------------------------------------------------------------ the reference's predict(), batched
+    def set_warm_start(self, u_init: Optional[torch.Tensor]) -> None:
+        """OPT-IN: start the next solves from `u_init` [B, N, 2] (e.g. the previous solution
+        shifted by one stage) instead of the reference's zero controls (agents/pure_mpc.py:240-246).
+        None restores the cold start.  Changes which local optimum is found -- keep off for parity."""
+        if u_init is None:
+            self._u_init = None
+            _capi.check(self._lib, self._h, self._lib.mpc_set_warm_start(self._h, None))
+            return
+        u = u_init.to(device=self.device, dtype=torch.float32).contiguous()
+        if u.dim() != 3 or tuple(u.shape[1:]) != (self.horizon, 2):
+            raise ValueError(f"u_init must be [B, {self.horizon}, 2]")
+        self._u_init = u
+        _capi.check(self._lib, self._h, self._lib.mpc_set_warm_start(self._h, u.data_ptr()))
+
+    @staticmethod
+    def shift_controls(U: torch.Tensor) -> torch.Tensor:
+        """Receding-horizon shift: u_k <- u_{k+1}, last stage repeated."""
+        return torch.cat([U[:, 1:], U[:, -1:]], dim=1).contiguous()
+
     def predict_batch(self, obs: torch.Tensor, ref_speed: Optional[torch.Tensor] = None,
                       weights: Optional[torch.Tensor] = None, reset_mask: Optional[torch.Tensor] = None,
                       return_controls: bool = False):

@@ -25,6 +25,7 @@ struct MpcHandle {
   void* ws_block = nullptr;       // one allocation carved into the BatchWs arrays
   BatchWs ws{};
   int* work_counter = nullptr;
+  const float* u_init = nullptr;   // opt-in warm start (device, borrowed)
   float* sink = nullptr;
   // host-call staging (mpc_predict_host)
   float* d_obs = nullptr; float* d_ref_speed = nullptr; float* d_weights = nullptr; uint8_t* d_reset = nullptr;
@@ -232,6 +233,7 @@ MPC_API int mpc_solve(MpcHandle* h, const MpcProblemBatch* batch, int B, const M
   CK(h, cudaMemsetAsync(h->work_counter, 0, sizeof(int), st));
   SolveLaunch s;
   s.cfg = h->scfg; s.batch = *batch; s.out = *out; s.B = B; s.work_counter = h->work_counter;
+  s.u_init = h->u_init;
   s.threads_per_block = h->tpb; s.smem_bytes = h->smem;
   int need = (B + h->tpb - 1) / h->tpb;
   s.grid = need < h->grid ? need : h->grid;
@@ -308,6 +310,12 @@ MPC_API int mpc_predict_host(MpcHandle* h, const float* obs_host, const float* r
   CK(h, cudaStreamSynchronize(st));
   if (h2d_bytes) *h2d_bytes = up;
   if (d2h_bytes) *d2h_bytes = down;
+  return MPC_OK;
+}
+
+MPC_API int mpc_set_warm_start(MpcHandle* h, const float* u_init) {
+  if (!h) return MPC_ERR_BAD_ARG;
+  h->u_init = u_init;
   return MPC_OK;
 }
 

@@ -50,6 +50,7 @@ struct SolveLaunch {
   MpcSolveOut out;
   int B;
   int* work_counter;      // device, zeroed before launch
+  const float* u_init;    // [B][N][2] warm start or null
   int threads_per_block;
   int grid;
   size_t smem_bytes;

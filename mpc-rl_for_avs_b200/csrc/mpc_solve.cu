@@ -94,7 +94,8 @@ __device__ __forceinline__ void load_problem(const MpcProblemBatch& b, int B, in
 // policy) and starts iterating on the next trip.
 template <int TPB>
 __global__ void __launch_bounds__(TPB, 1)
-k_solve(const SolverConfig cfg, const MpcProblemBatch batch, const MpcSolveOut out, const int B, int* __restrict__ work_counter) {
+k_solve(const SolverConfig cfg, const MpcProblemBatch batch, const MpcSolveOut out, const int B, int* __restrict__ work_counter,
+        const float* __restrict__ u_init) {
   extern __shared__ __align__(16) float smem[];
   const RefTab<float> ref = stage_tables(smem);
   using SL = Slots<float, true, TPB>;
@@ -114,6 +115,13 @@ k_solve(const SolverConfig cfg, const MpcProblemBatch batch, const MpcSolveOut o
       if (active) {
         load_problem(batch, B, idx, cfg, p, sl);
         solve_init(cfg, sl, s);
+        if (u_init) {                       // opt-in warm start: the first rollout clamps it into the node boxes
+#pragma unroll 1
+          for (int k = 0; k < cfg.N; ++k) {
+            sl.U(k, 0) = u_init[((size_t)idx * cfg.N + k) * 2];
+            sl.U(k, 1) = u_init[((size_t)idx * cfg.N + k) * 2 + 1];
+          }
+        }
         fresh = true;
       }
     }
@@ -167,7 +175,7 @@ template <int TPB> static cudaError_t launch_solve_t(const SolveLaunch& s, cudaS
     if (e != cudaSuccess) return e;
     configured = s.smem_bytes;
   }
-  k_solve<TPB><<<s.grid, TPB, s.smem_bytes, stream>>>(s.cfg, s.batch, s.out, s.B, s.work_counter);
+  k_solve<TPB><<<s.grid, TPB, s.smem_bytes, stream>>>(s.cfg, s.batch, s.out, s.B, s.work_counter, s.u_init);
   return cudaGetLastError();
 }
 

@@ -198,6 +198,11 @@ def test_every_converged_solution_is_confirmed_by_the_oracle(name, M, wd):
         if not ok:
             bad.append((int(i), du0, gain))
     assert not bad, bad
+    # solver-independent certificate: first-order (KKT) residual of the reference NLP at the GPU controls,
+    # multipliers by non-negative least squares over the constraints within 1e-4 of active
+    kkt = np.array([orc.kkt_residual(r["U"][i].astype(np.float64), r["probs"][i], 1e-4)[0] for i in idx])
+    scale = 1.0 + np.abs(r["cost64"][idx])
+    assert np.median(kkt / scale) <= 1e-5 and np.mean(kkt / scale <= 1e-3) >= 0.97, (np.median(kkt / scale), np.max(kkt / scale))
     # bounds of the reference NLP hold on every returned iterate, converged or not
     for i in range(len(r["probs"])):
         X = orc.rollout(r["probs"][i].s0, r["U"][i].astype(np.float64))
@@ -422,3 +427,41 @@ def test_config2_4096_no_collision_batch():
     for i in np.nonzero(st[:64] == 0)[0][:24]:
         ok, du0, gain = helpers.oracle_warm_confirms(probs[i], U[i])
         assert ok, (i, du0, gain)
+
+
+def test_opt_in_warm_start():
+    """receding-horizon warm start is opt-in.  Restarting from the shifted previous solution after the
+    scene advanced one step must converge in fewer iterations, still to oracle-confirmed local optima, and the
+    cold-start path must be unaffected once it is switched off."""
+    pkg = _pkg()
+    B, M = 256, 8
+    obs, _, _ = pkg.make_scenarios(B, M, seed=61, v_max=9.5)
+    agent = pkg.BatchedPureMPC(CFG, vehicles_count=M + 1, max_batch=B, collision_check=False, weight_distance=10.0)
+    a0, U0 = agent.predict_batch(obs.cuda(), return_controls=True)
+    a0, it0, st0 = a0.clone(), agent.iters[:B].clone(), agent.status[:B].clone()
+    # advance the ego along its first optimal control and the others at constant velocity (one policy step)
+    o = obs.numpy().copy()
+    U0n = U0.cpu().numpy()
+    for i in range(B):
+        s = np.array([o[i, 0, 1], o[i, 0, 2], o[i, 0, 5], np.hypot(o[i, 0, 3], o[i, 0, 4])], dtype=np.float64)
+        s1 = orc.step(s, U0n[i, 0].astype(np.float64), 0.1)
+        o[i, 0, 1], o[i, 0, 2], o[i, 0, 5] = s1[0], s1[1], s1[2]
+        o[i, 0, 3], o[i, 0, 4] = s1[3] * np.cos(s1[2]), s1[3] * np.sin(s1[2])
+    o[:, 1:, 1] += 0.1 * o[:, 1:, 3]
+    o[:, 1:, 2] += 0.1 * o[:, 1:, 4]
+    o1 = torch.from_numpy(o.astype(np.float32)).cuda()
+    a_cold = agent.predict_batch(o1).clone()
+    it_cold = agent.iters[:B].clone()
+    agent.set_warm_start(agent.shift_controls(U0))
+    a_warm, U_warm = agent.predict_batch(o1, return_controls=True)
+    it_warm, st_warm = agent.iters[:B].clone(), agent.status[:B].cpu().numpy()
+    both = (st0 == 0).cpu().numpy() & (st_warm == 0)
+    assert both.mean() > 0.7
+    assert it_warm[torch.from_numpy(both).cuda()].float().mean() < 0.7 * it_cold[torch.from_numpy(both).cuda()].float().mean()
+    probs, _ = helpers.problems_from_obs(o.astype(np.float32), w_distance=10.0)
+    Uw = U_warm.cpu().numpy()
+    for i in np.nonzero(both)[0][:16]:
+        ok, du0, gain = helpers.oracle_warm_confirms(probs[i], Uw[i])
+        assert ok, (i, du0, gain)
+    agent.set_warm_start(None)
+    assert torch.equal(agent.predict_batch(o1), a_cold)
