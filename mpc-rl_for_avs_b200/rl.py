@@ -1,0 +1,260 @@
+"""SURVEY 8-f "next" rows N1 + N2: a batched synthetic intersection environment and the batched
+A2C-MPC rollout / update loop (BASELINE config 4: 1024 vectorised envs, RL-set reference speed, MPC
+on the GPU).  NOT part of the hot path; plain PyTorch tensor code around `BatchedPureMPC`.
+
+What is mirrored from the reference (file:line in SaeedRahmani/MPC-RL_for_AVs):
+  * rollout structure of `A2C_MPC.collect_rollouts` (agents/a2c_mpc.py:111-180): policy(obs) -> RL action =
+    reference speed (v0) -> MPC -> env.step(raw (a, delta)) -> buffer stores the *RL* action;
+  * A2C hyper-parameters of config/cfg.yaml:30-45 (n_steps 64, lr 7e-4, RMSprop eps 1e-5, gamma 0.99,
+    gae_lambda 1.0, vf_coef 0.5, max_grad_norm 0.5, ent_coef 0) and the loss of agents/a2c_mpc.py:182-226;
+  * the policy's action space Box(-1, 1, (1,)) (trainers/trainer_utils.py:6-26), unclipped Gaussian samples
+    as A2C passes them -> clip(., 0, 30) inside update_reference_states;
+  * observation layout / ordering (config/config.py:10-26: Kinematics, absolute, sorted by distance);
+  * reward and termination rules of envs/intersection_env__.py:61-129 (collision -5, speed reward over
+    [7, 9] m/s, arrived +1, episode ends on crash / arrival / time limit);
+  * the action path of the SB3 subclasses: raw (a, delta) into highway-env's ContinuousAction, i.e. clipped
+    to [-1, 1] and scaled to +-5 m/s^2 / +-pi/4 (quirk Q8).
+
+What is a STAND-IN (highway-env is not installable here): other vehicles drive straight at constant speed
+on the four approach lanes and are respawned when they leave the map; collisions are a 2.5 m centre distance
+test; "arrived" is reaching the end of the hard-coded path.
+"""
+from __future__ import annotations
+
+import math
+import time
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from .scenarios import reference_path
+
+_LANE_HEADING = (-math.pi / 2, 0.0, math.pi / 2, math.pi)
+
+
+class BatchedIntersectionEnv:
+    """B independent intersection scenes as tensors on one device (CPU works too: used by the CPU tests)."""
+
+    def __init__(self, n_envs: int, n_others: int = 9, device="cuda", seed: int = 0, policy_frequency: int = 10,
+                 simulation_frequency: int = 30, duration_steps: int = 100, action_scaling: str = "sb3_raw"):
+        self.B, self.M, self.V = int(n_envs), int(n_others), int(n_others) + 1
+        self.device = torch.device(device)
+        self.gen = torch.Generator(device=self.device)
+        self.gen.manual_seed(seed)
+        self.sub = simulation_frequency // policy_frequency
+        self.dt_sim = 1.0 / simulation_frequency
+        self.duration_steps = duration_steps
+        self.action_scaling = action_scaling
+        ref = torch.from_numpy(reference_path(1.0 / policy_frequency)).to(self.device)
+        self.ref_xy = ref[:, :2].float()
+        f = dict(device=self.device, dtype=torch.float32)
+        self.ego = torch.zeros(self.B, 4, **f)               # x, y, heading, speed
+        self.oth = torch.zeros(self.B, self.M, 4, **f)       # x, y, speed, heading
+        self.t = torch.zeros(self.B, dtype=torch.int32, device=self.device)
+        self.crashed = torch.zeros(self.B, dtype=torch.bool, device=self.device)
+        self.reset()
+
+    # ----------------------------------------------------------------------------------------------
+    def _rand(self, *shape):
+        return torch.rand(*shape, generator=self.gen, device=self.device)
+
+    def _randn(self, *shape):
+        return torch.randn(*shape, generator=self.gen, device=self.device)
+
+    def _spawn_others(self, n: int) -> torch.Tensor:
+        c = torch.randint(0, 4, (n, self.M), generator=self.gen, device=self.device)
+        lane = 2.0 + 0.2 * self._randn(n, self.M)
+        d = -30.0 + 100.0 * self._rand(n, self.M)
+        ang = c.float() * (math.pi / 2)
+        px = torch.cos(ang) * lane - torch.sin(ang) * d
+        py = torch.sin(ang) * lane + torch.cos(ang) * d
+        spd = torch.clamp(8.0 + self._randn(n, self.M), min=0.5)
+        hd = torch.tensor(_LANE_HEADING, device=self.device)[c]
+        return torch.stack([px, py, spd, hd], dim=-1)
+
+    def reset(self, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        m = torch.ones(self.B, dtype=torch.bool, device=self.device) if mask is None else mask.to(self.device).bool()
+        n = int(m.sum())
+        if n:
+            ego = torch.zeros(n, 4, device=self.device)
+            ego[:, 0] = 2.0 + 0.1 * self._randn(n)
+            ego[:, 1] = 50.0 + self._rand(n)                 # envs/intersection_env__.py:303-315: spawns at the south entry
+            ego[:, 2] = -math.pi / 2
+            ego[:, 3] = 8.0 + 2.0 * self._rand(n)
+            oth = self._spawn_others(n)
+            near = torch.hypot(oth[..., 0] - ego[:, None, 0], oth[..., 1] - ego[:, None, 1]) < 8.0
+            oth[..., 1] = torch.where(near & (oth[..., 3] == -math.pi / 2), oth[..., 1] - 20.0, oth[..., 1])
+            self.ego[m], self.oth[m] = ego, oth
+            self.t[m] = 0
+            self.crashed[m] = False
+        return self.observe()
+
+    def observe(self) -> torch.Tensor:
+        """[B, V, 8] Kinematics rows (presence, x, y, vx, vy, heading, sin_h, cos_h), ego first, others sorted by
+        distance to the ego (config/config.py:13, cfg.yaml:4-6)."""
+        e, o = self.ego, self.oth
+        dist_ = torch.hypot(o[..., 0] - e[:, None, 0], o[..., 1] - e[:, None, 1])
+        idx = torch.argsort(dist_, dim=1)
+        o = torch.gather(o, 1, idx[..., None].expand(-1, -1, 4))
+        obs = torch.zeros(self.B, self.V, 8, device=self.device)
+        obs[:, :, 0] = 1.0
+        obs[:, 0, 1], obs[:, 0, 2] = e[:, 0], e[:, 1]
+        obs[:, 0, 3], obs[:, 0, 4] = e[:, 3] * torch.cos(e[:, 2]), e[:, 3] * torch.sin(e[:, 2])
+        obs[:, 0, 5], obs[:, 0, 6], obs[:, 0, 7] = e[:, 2], torch.sin(e[:, 2]), torch.cos(e[:, 2])
+        obs[:, 1:, 1], obs[:, 1:, 2] = o[..., 0], o[..., 1]
+        obs[:, 1:, 3], obs[:, 1:, 4] = o[..., 2] * torch.cos(o[..., 3]), o[..., 2] * torch.sin(o[..., 3])
+        obs[:, 1:, 5], obs[:, 1:, 6], obs[:, 1:, 7] = o[..., 3], torch.sin(o[..., 3]), torch.cos(o[..., 3])
+        return obs.contiguous()
+
+    def step(self, action: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, Dict[str, torch.Tensor]]:
+        """action [B, 2] = (accel, steer) as the caller sends it.  Returns (obs, reward, done, info); finished
+        environments are reset in place (VecEnv semantics) and flagged in `done`."""
+        a = action.to(self.device).float()
+        if self.action_scaling == "sb3_raw":               # agents/a2c_mpc.py:151-153 -> ContinuousAction clip + lmap (quirk Q8)
+            acc = a[:, 0].clamp(-1, 1) * 5.0
+            steer = a[:, 1].clamp(-1, 1) * (math.pi / 4)
+        elif self.action_scaling == "physical":
+            acc, steer = a[:, 0].clamp(-5, 5), a[:, 1].clamp(-math.pi / 4, math.pi / 4)
+        else:
+            raise ValueError("action_scaling must be 'sb3_raw' or 'physical'")
+        x, y, th, v = self.ego.unbind(1)
+        beta = torch.atan(0.5 * torch.tan(steer))
+        for _ in range(self.sub):                          # highway-env Vehicle.step at the simulation frequency
+            x = x + v * torch.cos(th + beta) * self.dt_sim
+            y = y + v * torch.sin(th + beta) * self.dt_sim
+            th = th + v * torch.sin(beta) / 2.5 * self.dt_sim
+            v = (v + acc * self.dt_sim).clamp(-40.0, 40.0)
+        th = torch.atan2(torch.sin(th), torch.cos(th))
+        self.ego = torch.stack([x, y, th, v], dim=1)
+        o = self.oth
+        step_len = o[..., 2] * (self.sub * self.dt_sim)
+        ox = o[..., 0] + step_len * torch.cos(o[..., 3])
+        oy = o[..., 1] + step_len * torch.sin(o[..., 3])
+        gone = (ox.abs() > 90) | (oy.abs() > 90)
+        if bool(gone.any()):                               # _clear_vehicles + _spawn_vehicle stand-in
+            fresh = self._spawn_others(self.B)
+            far = fresh                                     # same lane geometry, placed at the map edge
+            far[..., 0] = torch.where(far[..., 3] == 0.0, -80.0, torch.where(far[..., 3] == math.pi, 80.0, far[..., 0]))
+            far[..., 1] = torch.where(far[..., 3] == -math.pi / 2, 80.0, torch.where(far[..., 3] == math.pi / 2, -80.0, far[..., 1]))
+            ox, oy = torch.where(gone, far[..., 0], ox), torch.where(gone, far[..., 1], oy)
+            o = torch.where(gone[..., None], far, o)
+        self.oth = torch.stack([ox, oy, o[..., 2], o[..., 3]], dim=-1)
+        self.t += 1
+        crashed = (torch.hypot(ox - x[:, None], oy - y[:, None]) < 2.5).any(dim=1)
+        arrived = (x <= self.ref_xy[-2, 0]) & ((y - self.ref_xy[-1, 1]).abs() < 4.0)
+        speed_r = ((v - 7.0) / 2.0).clamp(0, 1)            # lmap(speed, [7, 9], [0, 1]) clipped
+        reward = -5.0 * crashed.float() + 1.0 * speed_r
+        reward = torch.where(arrived, torch.ones_like(reward), reward)
+        truncated = self.t >= self.duration_steps
+        done = crashed | arrived | truncated
+        info = {"crashed": crashed, "arrived": arrived, "truncated": truncated, "speed": v.clone()}
+        obs = self.reset(done) if bool(done.any()) else self.observe()
+        return obs, reward, done, info
+
+
+class ActorCritic(nn.Module):
+    """SB3 `MlpPolicy` shape for A2C: separate 64-64 tanh towers, state-independent log-std
+    (trainers/trainer_utils.py:6-26 builds the same policy with Box(-1, 1, (action_dim,)))."""
+
+    def __init__(self, obs_dim: int, action_dim: int = 1):
+        super().__init__()
+        self.pi = nn.Sequential(nn.Linear(obs_dim, 64), nn.Tanh(), nn.Linear(64, 64), nn.Tanh(), nn.Linear(64, action_dim))
+        self.vf = nn.Sequential(nn.Linear(obs_dim, 64), nn.Tanh(), nn.Linear(64, 64), nn.Tanh(), nn.Linear(64, 1))
+        self.log_std = nn.Parameter(torch.zeros(action_dim))
+
+    def dist(self, obs):
+        return torch.distributions.Normal(self.pi(obs), self.log_std.exp())
+
+    def forward(self, obs):
+        d = self.dist(obs)
+        a = d.sample()
+        return a, self.vf(obs).squeeze(-1), d.log_prob(a).sum(-1)
+
+
+class A2CMPC:
+    """Batched counterpart of `A2C_MPC` v0 (agents/a2c_mpc.py): the policy's action is the MPC's reference speed."""
+
+    def __init__(self, env: BatchedIntersectionEnv, mpc, n_steps: int = 64, lr: float = 7e-4, gamma: float = 0.99,
+                 gae_lambda: float = 1.0, ent_coef: float = 0.0, vf_coef: float = 0.5, max_grad_norm: float = 0.5,
+                 rms_prop_eps: float = 1e-5, seed: int = 0):
+        self.env, self.mpc = env, mpc
+        self.n_steps, self.gamma, self.lam = n_steps, gamma, gae_lambda
+        self.ent_coef, self.vf_coef, self.max_grad_norm = ent_coef, vf_coef, max_grad_norm
+        torch.manual_seed(seed)
+        self.policy = ActorCritic(env.V * 8, 1).to(env.device)
+        if dist.is_available() and dist.is_initialized():
+            for p in self.policy.parameters():
+                dist.broadcast(p.data, 0)
+        self.opt = torch.optim.RMSprop(self.policy.parameters(), lr=lr, alpha=0.99, eps=rms_prop_eps)
+        self.obs = env.observe()
+        self.episode_start = torch.ones(env.B, dtype=torch.bool, device=env.device)
+        self.stats = {"mpc_s": 0.0, "env_s": 0.0, "policy_s": 0.0, "update_s": 0.0, "steps": 0}
+
+    def collect_rollouts(self):
+        B, T, dev = self.env.B, self.n_steps, self.env.device
+        buf = {k: torch.zeros(T, B, device=dev) for k in ("act", "rew", "val", "logp", "done")}
+        obs_buf = torch.zeros(T, B, self.env.V * 8, device=dev)
+        cuda = dev.type == "cuda"
+        for t in range(T):
+            t0 = time.perf_counter()
+            with torch.no_grad():
+                flat = self.obs.reshape(B, -1)
+                a, v, lp = self.policy(flat)
+            if cuda:
+                torch.cuda.synchronize(dev)
+            t1 = time.perf_counter()
+            # v0: RL action = reference speed (agents/a2c_mpc.py:138-150); the latch of finished envs is cleared
+            mpc_action = self.mpc.predict_batch(self.obs, ref_speed=a, reset_mask=self.episode_start)
+            if cuda:
+                torch.cuda.synchronize(dev)
+            t2 = time.perf_counter()
+            new_obs, rew, done, _ = self.env.step(mpc_action)
+            if cuda:
+                torch.cuda.synchronize(dev)
+            t3 = time.perf_counter()
+            obs_buf[t], buf["act"][t], buf["rew"][t], buf["val"][t], buf["logp"][t] = flat, a.squeeze(-1), rew, v, lp
+            buf["done"][t] = done.float()
+            self.obs, self.episode_start = new_obs, done
+            self.stats["policy_s"] += t1 - t0
+            self.stats["mpc_s"] += t2 - t1
+            self.stats["env_s"] += t3 - t2
+            self.stats["steps"] += B
+        with torch.no_grad():
+            last_v = self.policy.vf(self.obs.reshape(B, -1)).squeeze(-1)
+        adv = torch.zeros(T, B, device=dev)
+        gae = torch.zeros(B, device=dev)
+        for t in reversed(range(T)):                        # SB3 RolloutBuffer.compute_returns_and_advantage
+            nv = last_v if t == T - 1 else buf["val"][t + 1]
+            nonterminal = 1.0 - buf["done"][t]
+            delta = buf["rew"][t] + self.gamma * nv * nonterminal - buf["val"][t]
+            gae = delta + self.gamma * self.lam * nonterminal * gae
+            adv[t] = gae
+        return obs_buf, buf, adv, adv + buf["val"]
+
+    def train_step(self) -> Dict[str, float]:
+        obs_buf, buf, adv, ret = self.collect_rollouts()
+        t0 = time.perf_counter()
+        flat = obs_buf.reshape(-1, obs_buf.shape[-1])
+        d = self.policy.dist(flat)
+        logp = d.log_prob(buf["act"].reshape(-1, 1)).sum(-1)
+        values = self.policy.vf(flat).squeeze(-1)
+        policy_loss = -(adv.reshape(-1) * logp).mean()
+        value_loss = torch.nn.functional.mse_loss(ret.reshape(-1), values)
+        entropy_loss = -d.entropy().sum(-1).mean()
+        loss = policy_loss + self.ent_coef * entropy_loss + self.vf_coef * value_loss
+        self.opt.zero_grad()
+        loss.backward()
+        if dist.is_available() and dist.is_initialized():   # data-parallel update over the env shards
+            w = dist.get_world_size()
+            for p in self.policy.parameters():
+                dist.all_reduce(p.grad)
+                p.grad /= w
+        nn.utils.clip_grad_norm_(self.policy.parameters(), self.max_grad_norm)
+        self.opt.step()
+        if self.env.device.type == "cuda":
+            torch.cuda.synchronize(self.env.device)
+        self.stats["update_s"] += time.perf_counter() - t0
+        return {"loss": float(loss.detach()), "policy_loss": float(policy_loss.detach()), "value_loss": float(value_loss.detach()),
+                "mean_reward": float(buf["rew"].mean()), "done_rate": float(buf["done"].mean())}
