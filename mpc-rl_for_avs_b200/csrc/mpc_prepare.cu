@@ -43,6 +43,10 @@ cudaError_t upload_ref_table_prepare() {
 }
 
 __device__ __forceinline__ double norm2(double dx, double dy) { return sqrt(dx * dx + dy * dy); }
+// argmin over distances compares the squared norms: sqrt is monotone, so the first minimum is the same index
+// unless two squared distances differ by less than the sqrt's rounding (~1 ulp) -- and FP64 sqrt is a
+// ~20-instruction software sequence that used to dominate this kernel
+__device__ __forceinline__ double dist2(double dx, double dy) { return dx * dx + dy * dy; }
 __device__ __forceinline__ double orient(double ax, double ay, double bx, double by, double cx, double cy) {
   return (bx - ax) * (cy - ay) - (by - ay) * (cx - ax);
 }
@@ -81,7 +85,7 @@ k_prepare(const PrepareParams P) {
   double bd = 1e300;
   int bj = 0;
   for (int j = l; j < kNRef; j += LPP) {
-    double d = norm2(ex - c_refd[j][0], ey - c_refd[j][1]);
+    double d = dist2(ex - c_refd[j][0], ey - c_refd[j][1]);
     if (d < bd) { bd = d; bj = j; }
   }
 #pragma unroll
@@ -212,8 +216,8 @@ k_prepare(const PrepareParams P) {
           // nearest-time test (agents/pure_mpc.py:641-649), first minimum wins
           int te = 0, to = 0;
           double bde = 1e300, bdo = 1e300;
-          for (int t = 0; t < ne; ++t) { double d = norm2(s_ex[g][t] - cx, s_ey[g][t] - cy); if (d < bde) { bde = d; te = t; } }
-          for (int t = 0; t <= kPred; ++t) { double d = norm2(Ox[t] - cx, Oy[t] - cy); if (d < bdo) { bdo = d; to = t; } }
+          for (int t = 0; t < ne; ++t) { double d = dist2(s_ex[g][t] - cx, s_ey[g][t] - cy); if (d < bde) { bde = d; te = t; } }
+          for (int t = 0; t <= kPred; ++t) { double d = dist2(Ox[t] - cx, Oy[t] - cy); if (d < bdo) { bdo = d; to = t; } }
           int dtm = te - to; dtm = dtm < 0 ? -dtm : dtm;
           if (dtm < kTimeThreshold) {
             // candidates are visited in lexicographic (x, y) order: keep the smallest passing one
@@ -224,7 +228,7 @@ k_prepare(const PrepareParams P) {
       if (have) {
         my_flag = 1;
         double bdr = 1e300;
-        for (int j = 0; j < kNRef; ++j) { double d = norm2(c_refd[j][0] - qx, c_refd[j][1] - qy); if (d < bdr) { bdr = d; my_cidx = j; } }
+        for (int j = 0; j < kNRef; ++j) { double d = dist2(c_refd[j][0] - qx, c_refd[j][1] - qy); if (d < bdr) { bdr = d; my_cidx = j; } }
       }
     }
   }
