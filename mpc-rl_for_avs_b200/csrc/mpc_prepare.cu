@@ -130,17 +130,22 @@ k_prepare(const PrepareParams P) {
     int n_valid = 0;                                   // how many of t = 1..30 produce a point
     if (len >= 2) {
       const double vref = c_refd[ego_index][2];
+      // each lane owns the points t = 1 + l, 1 + l + LPP, ...; the speed ramp, the travelled distance and the
+      // arc-length walk are all monotone in t, so they continue from the lane's previous point (same
+      // sequential sums as the reference, evaluated once)
+      double cur = ev, dist = 0.0;
+      int t_done = 0;
+      int idx = 0;
+      double cum = 0.0, prev = 0.0;
       for (int t = 1 + l; t <= kPred; t += LPP) {
-        double cur = ev, dist = 0.0;
-        for (int i = 1; i <= t; ++i) {                 // same sequential sums as the reference
+        for (int i = t_done + 1; i <= t; ++i) {
           if (cur < vref) { double nv = cur + kMaxAccPred * P.dt; cur = nv < vref ? nv : vref; }
           else cur = vref;
           dist += cur * P.dt;
         }
+        t_done = t;
         // left searchsorted over cum[0..len-1], cum[0] = 0, cum[i] = cum[i-1] + seg[start+i-1]
-        int idx = 0;
-        double cum = 0.0, prev = 0.0;
-        while (cum < dist) {
+        while (idx < len && cum < dist) {
           ++idx;
           if (idx >= len) break;
           prev = cum;
