@@ -799,6 +799,9 @@ template <typename T> MPC_HD bool accept_step(T J, T Jn, T expected) {
 // Line search: ONE pass of two candidates (alpha, alpha/4).  A second pass (1/16, 1/64 ...) rescued only
 // ~3 % of the iterations but, because a warp waits for its slowest lane, was executed in almost every
 // trip: dropping it costs 0.4 % converged problems and saves 22 % of the launch (profiles/r01_solve_kernel_history.md).
+#ifndef MPC_LS_NA
+#define MPC_LS_NA 2
+#endif
 #ifndef MPC_LS_RATIO
 #define MPC_LS_RATIO 0.25
 #endif
@@ -836,11 +839,18 @@ MPC_HD void after_line_search(const SolverConfig& cfg, SolveState<T>& s, bool ac
 template <typename T, typename SL>
 MPC_HD bool line_search_pass(const SolverConfig& cfg, const ProblemScalars<T>& p, const RefTab<T>& ref,
                              const SL& sl, SolveState<T>& s, T d1, T d2, T& alpha, T& Jacc, T& mdacc) {
+#if MPC_LS_NA == 1
+  T Jt, mt;
+  forward_pass<T, 1, SL>(cfg, p, ref, sl, &alpha, false, true, &Jt, &mt);
+  s.trials += 1;
+  if (accept_step(s.J, Jt, alpha * d1 + alpha * alpha * d2)) { Jacc = Jt; mdacc = mt; return true; }
+#else
   T al[2] = {alpha, alpha * T(MPC_LS_RATIO)}, Jt[2], mt[2];
   forward_pass<T, 2, SL>(cfg, p, ref, sl, al, false, true, Jt, mt);
   s.trials += 2;
   if (accept_step(s.J, Jt[0], al[0] * d1 + al[0] * al[0] * d2)) { alpha = al[0]; Jacc = Jt[0]; mdacc = mt[0]; return true; }
   if (accept_step(s.J, Jt[1], al[1] * d1 + al[1] * al[1] * d2)) { alpha = al[1]; Jacc = Jt[1]; mdacc = mt[1]; return true; }
+#endif
   alpha = alpha * T(MPC_LS_RATIO) * T(MPC_LS_RATIO);
   return false;
 }
