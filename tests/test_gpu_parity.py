@@ -465,3 +465,36 @@ def test_opt_in_warm_start():
         assert ok, (i, du0, gain)
     agent.set_warm_start(None)
     assert torch.equal(agent.predict_batch(o1), a_cold)
+
+
+def test_collision_flags_exact_on_4096_scenes():
+    """Bit-exactness of the FP64 collision kernel at scale: ego row, per-vehicle flags, conflict rows, stop row and
+    the regenerated profile against the oracle on 4096 seeded scenes (degenerate geometry excluded and counted)."""
+    pkg = _pkg()
+    B, M = 4096, 8
+    obs, _, _ = pkg.make_scenarios(B, M, seed=77)
+    agent = pkg.BatchedPureMPC(CFG, vehicles_count=M + 1, max_batch=B, collision_check=True)
+    ws = {k: v.cpu().numpy() for k, v in agent.prepare_batch(obs.cuda()).items()}
+    flags = agent.agent_collide[:B].cpu().numpy().astype(bool)
+    cidx = agent.conflict_index[:B].cpu().numpy()
+    stop = agent.stop_index[:B].cpu().numpy()
+    ego_idx = agent.ego_index[:B].cpu().numpy()
+    o = obs.numpy()
+    n_deg = n_col = 0
+    for i in range(B):
+        parsed = orc.parse_obs(o[i], M + 1)
+        res = orc.detect_collisions(parsed.ego, parsed.others)
+        assert ego_idx[i] == orc.nearest_index(parsed.ego[:2], helpers.REF[:, :2]), i
+        if res.degenerate:
+            n_deg += 1
+            continue
+        assert list(flags[i]) == list(res.agent_collide), i
+        assert [int(c) for c in cidx[i]] == [(-1 if c is None else int(c)) for c in res.conflict_index], i
+        assert bool(ws["is_collide"][i]) == res.is_collide, i
+        col, st = orc.regenerate_ref_speed(int(ego_idx[i]), parsed.ego[3], res.is_collide, res.conflict_index)
+        assert int(stop[i]) == (-1 if st is None else st), i
+        j = np.minimum(ego_idx[i] + np.arange(20), 84)
+        prof = _profile({k: v[i:i + 1] for k, v in ws.items() if k.startswith("vr_")})[0]
+        assert np.allclose(prof, col[j], rtol=1e-6, atol=1e-5), i
+        n_col += res.is_collide
+    assert n_deg <= 0.02 * B and n_col >= 0.1 * B, (n_deg, n_col)
