@@ -26,6 +26,10 @@ CFG = {"horizon": H, "weight_speed": 1.0, "weight_control": 1.0, "weight_input_d
 WORKLOAD = "config3: 65536 synthetic intersection problems/GPU, H=20, 8 obstacles, distance cost 10, collision check + ref-speed regeneration"
 
 
+def workload(batch: int) -> str:
+    return WORKLOAD if batch == 65536 else WORKLOAD.replace("65536", str(batch)) + " (non-default --batch)"
+
+
 def flops_per_solve(mean_iters: float, m: int = M, h: int = H, latched_frac: float = 0.0) -> float:
     """SURVEY 8-d yardstick: F_solve = I*H*(960+47M) + 18.7k*M per un-latched collision check."""
     return mean_iters * h * (960 + 47 * m) + (1.0 - latched_frac) * 18.7e3 * m
@@ -268,7 +272,7 @@ def main() -> None:
     line = {"metric": "mpc_solves_per_sec", "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "horizon": H, "obstacles": M,
+            "config": {"workload": workload(B), "batch_per_gpu": B, "horizon": H, "obstacles": M,
                        "l2": "inputs rotate over 8 distinct batches (8 x 19.4 MB > the 126 MB L2); "
                              "the per-step working set is on-chip, HBM traffic is the compulsory ~0.3 KB/problem",
                        "parallelism": f"env-sharded x{world}" + (", all_gather(actions)" if world > 1 else "")},
