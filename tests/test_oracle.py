@@ -56,6 +56,20 @@ def test_multiple_shooting_form_agrees():
     assert np.max(np.abs(a.u0 - b.u0)) < 1e-5 and abs(a.cost - b.cost) < 1e-6 * a.cost
 
 
+def test_multiple_shooting_form_agrees_on_golden_sample():
+    """Same cross-check on fixture problems (incl. RL speed overrides): the reference's own NLP layout and the
+    single-shooting form reach the same optimum (cost to 1e-6 relative, first control to 1e-4)."""
+    g = helpers.load_golden("golden_track")
+    probs, _ = helpers.problems_from_obs(g["obs"][:40], g["ref_speed"][:40], g["has_ref_speed"][:40])
+    same = n = 0
+    for i in range(0, 40, 5):
+        a, b = orc.solve_nlp(probs[i]), orc.solve_nlp_multiple_shooting(probs[i])
+        n += 1          # (SLSQP's success flag is not used: on the 124-variable form it often stops on its precision test)
+        rel = abs(a.cost - b.cost) / max(1.0, abs(a.cost))
+        same += rel < 1e-6 and np.max(np.abs(a.u0 - b.u0)) < 1e-4
+    assert same >= n - 1, (n, same)
+
+
 def test_gradient_matches_finite_differences():
     rng = np.random.default_rng(0)
     others = np.array([[6.0, 40.0, 8.0, -np.pi / 2], [-3.0, 33.0, 7.0, 0.0]])
