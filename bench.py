@@ -239,6 +239,9 @@ def main() -> None:
         return
 
     # ---- roofline of the dominant kernel (k_solve), FP32 non-tensor ------------------------------------
+    sc = agent.solve_config()
+    tpb = sc["threads_small_batch"] if B < 500000 else sc["threads_large_batch"]
+    kernel_name = ("k_solve_tmem<%d>" if sc["gains_in_tmem"] else "k_solve<%d>") % tpb
     peak_tf = agent.fp32_peak_tflops(5)
     solve_ms = kt["solve_ms"]
     alg_flops = flops_per_solve(mean_iters) * B - 18.7e3 * M * B      # collision-check flops belong to k_prepare

@@ -55,7 +55,7 @@ class MpcCollisionOut(C.Structure):
 
 EXPORTS = ["mpc_create", "mpc_destroy", "mpc_last_error", "mpc_workspace_batch", "mpc_rollout_cost", "mpc_solve",
            "mpc_prepare", "mpc_predict", "mpc_predict_host", "mpc_launch_count", "mpc_fp32_peak", "mpc_timing_begin",
-           "mpc_timing_end", "mpc_device_info", "mpc_set_warm_start"]
+           "mpc_timing_end", "mpc_device_info", "mpc_set_warm_start", "mpc_solve_config"]
 
 
 class MpcError(RuntimeError):
@@ -106,6 +106,8 @@ def load() -> C.CDLL:
     lib.mpc_timing_begin.restype = C.c_int
     lib.mpc_timing_end.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.mpc_timing_end.restype = C.c_int
+    lib.mpc_solve_config.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.mpc_solve_config.restype = C.c_int
     lib.mpc_device_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.mpc_device_info.restype = C.c_int
     _lib = lib

@@ -2,6 +2,7 @@
 // Host side only: argument checks, workspace ownership, launch sequencing, error text.
 // No exception crosses the ABI; there is no CPU compute path anywhere in this library.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -21,6 +22,10 @@ struct MpcHandle {
   int sm_count = 0, cc_major = 0, cc_minor = 0, smem_optin = 0;
   int tpb = 0, grid = 0;
   size_t smem = 0;
+  int use_tmem = 0;
+  int tpb_small = 0;              // TMEM kernel: block size used below kBigBatch problems per launch
+  size_t smem_small = 0;
+  bool tpb_forced = false;
   // device workspace
   void* ws_block = nullptr;       // one allocation carved into the BatchWs arrays
   BatchWs ws{};
@@ -115,16 +120,45 @@ MPC_API int mpc_create(const MpcConfig* cfg, int device, int max_batch, MpcHandl
   } while (0)
 
   CKC(cudaSetDevice(device));
-  // grid / block: as many problems resident per SM as the slot file allows
-  int tpb = cfg->threads_per_block > 0 ? cfg->threads_per_block : 192;
-  tpb = (tpb + 31) / 32 * 32;
-  if (tpb > 192) tpb = 192;
-  while (tpb > 32 && solve_smem_bytes(N, M, tpb) > (size_t)h->smem_optin) tpb -= 32;
-  if (solve_smem_bytes(N, M, tpb) > (size_t)h->smem_optin) { fail(nullptr, MPC_ERR_BAD_ARG, "mpc_create: horizon/obstacle count do not fit shared memory"); mpc_destroy(h); return MPC_ERR_BAD_ARG; }
-  h->tpb = tpb;
-  h->smem = solve_smem_bytes(N, M, tpb);
+  // grid / block: as many problems resident per SM as the on-chip storage allows.  Default: gains in
+  // tensor memory (352 problems / SM at H=20, M=8); MPC_USE_TMEM=0 or a horizon whose gains do not fit the
+  // 512 TMEM columns selects the shared-memory kernel (192 problems / SM).
+  const char* env_tmem = getenv("MPC_USE_TMEM");
+  int want_tmem = env_tmem ? atoi(env_tmem) : 1;
+  int tpb = 0;
+  if (want_tmem) {
+    static const int cand[] = {384, 352, 320, 288, 256, 192, 128};
+    const int cap = cfg->threads_per_block > 0 ? cfg->threads_per_block : 384;
+    for (int c : cand) {
+      if (c > cap) continue;
+      if (!tmem_layout_fits(N, c)) continue;
+      if (solve_smem_bytes_tmem(N, M, c) > (size_t)h->smem_optin) continue;
+      if (65536 / c < 160) continue;                       // registers: the kernel needs ~150 per thread
+      tpb = c;
+      break;
+    }
+    if (tpb) {
+      h->use_tmem = 1; h->tpb = tpb; h->smem = solve_smem_bytes_tmem(N, M, tpb);
+      // Measured (profiles/r01_solve_kernel_history.md): 8 warps / SM (2 per scheduler, evenly) is the fastest
+      // block up to ~0.5 M problems per launch -- the launch is bounded by the latency of its longest problems,
+      // which grows with the number of resident warps; the largest block only pays off when throughput bound.
+      h->tpb_forced = cfg->threads_per_block > 0;
+      h->tpb_small = tpb < 256 ? tpb : 256;
+      h->smem_small = solve_smem_bytes_tmem(N, M, h->tpb_small);
+    }
+  }
+  if (!h->use_tmem) {
+    tpb = cfg->threads_per_block > 0 ? cfg->threads_per_block : 192;
+    tpb = (tpb + 31) / 32 * 32;
+    if (tpb > 192) tpb = 192;
+    while (tpb > 32 && solve_smem_bytes(N, M, tpb) > (size_t)h->smem_optin) tpb -= 32;
+    if (solve_smem_bytes(N, M, tpb) > (size_t)h->smem_optin) { fail(nullptr, MPC_ERR_BAD_ARG, "mpc_create: horizon/obstacle count do not fit shared memory"); mpc_destroy(h); return MPC_ERR_BAD_ARG; }
+    h->tpb = tpb;
+    h->smem = solve_smem_bytes(N, M, tpb);
+  }
   int bps = cfg->blocks_per_sm > 0 ? cfg->blocks_per_sm : (int)((size_t)prop.sharedMemPerMultiprocessor / (h->smem + 1024));
   if (bps < 1) bps = 1;
+  if (h->use_tmem) bps = 1;                                 // the CTA owns all 512 TMEM columns of its SM
   h->grid = h->sm_count * bps;
   CKC(configure_solve_kernel(h->smem));
   CKC(upload_ref_table_solve());
@@ -165,6 +199,14 @@ MPC_API int mpc_create(const MpcConfig* cfg, int device, int max_batch, MpcHandl
   CKC(cudaDeviceSynchronize());
 #undef CKC
   *out = h;
+  return MPC_OK;
+}
+
+MPC_API int mpc_solve_config(const MpcHandle* h, int* gains_in_tmem, int* threads_small_batch, int* threads_large_batch) {
+  if (!h) return MPC_ERR_BAD_ARG;
+  if (gains_in_tmem) *gains_in_tmem = h->use_tmem;
+  if (threads_small_batch) *threads_small_batch = (h->use_tmem && !h->tpb_forced) ? h->tpb_small : h->tpb;
+  if (threads_large_batch) *threads_large_batch = h->tpb;
   return MPC_OK;
 }
 
@@ -234,11 +276,12 @@ MPC_API int mpc_solve(MpcHandle* h, const MpcProblemBatch* batch, int B, const M
   SolveLaunch s;
   s.cfg = h->scfg; s.batch = *batch; s.out = *out; s.B = B; s.work_counter = h->work_counter;
   s.u_init = h->u_init;
-  s.threads_per_block = h->tpb; s.smem_bytes = h->smem;
-  int need = (B + h->tpb - 1) / h->tpb;
+  s.threads_per_block = h->tpb; s.smem_bytes = h->smem; s.use_tmem = h->use_tmem;
+  if (h->use_tmem && !h->tpb_forced && B < 500000) { s.threads_per_block = h->tpb_small; s.smem_bytes = h->smem_small; }
+  int need = (B + s.threads_per_block - 1) / s.threads_per_block;
   s.grid = need < h->grid ? need : h->grid;
   if ((rc = timed_begin(h, h->ev_solve, st))) return rc;
-  CK(h, launch_solve(s, st));
+  CK(h, h->use_tmem ? launch_solve_tmem(s, st) : launch_solve(s, st));
   if ((rc = timed_end(h, h->ev_solve, st))) return rc;
   h->launches += 1;
   return MPC_OK;

@@ -222,6 +222,7 @@ template <typename T, bool kPack, int kStride = 0> struct Slots {
       at(o + 12) = k0; at(o + 13) = k1;
     }
   }
+  MPC_HD void gains_fence() const {}
   MPC_HD void load_gains(int k, T& k0, T& k1, T (&Kr)[12]) const {
     const int o = oG() + kGainWords * k;
     if (kPack) {
@@ -241,6 +242,55 @@ template <typename T, bool kPack, int kStride = 0> struct Slots {
     }
   }
 };
+#if defined(__CUDACC__)
+// ---- slot file with the gains in TENSOR MEMORY (Blackwell TMEM, 256 KB / SM) ------------------------
+// tcgen05.ld/st with shape 32x32b give every thread of a warp a private 32-bit cell per TMEM column
+// (lane = 32 (warp % 4) + laneid), i.e. TMEM is usable as a per-thread scratchpad with 12-cycle loads.  The
+// 7 gain words of a stage live in 8 consecutive columns of the warp's own column range, so the shared-
+// memory footprint of a problem drops from 296 to 156 words and 352 instead of 192 problems stay
+// resident per SM.  The instructions are warp-collective (.sync.aligned, one column address for the
+// warp): the kernel that uses this type runs every sweep with all 32 lanes (k_solve_tmem).
+template <int kStride> struct SlotsTmem {
+  float* base;
+  uint32_t taddr;        // (lane quarter << 16) | first column of this warp's range
+  int N, M;
+  static constexpr bool kTmem = true;
+  __device__ __forceinline__ float& at(int s) const { return base[(unsigned)s * (unsigned)kStride]; }
+  __device__ __forceinline__ int oU() const { return 0; }
+  __device__ __forceinline__ int oX() const { return 2 * N; }
+  __device__ __forceinline__ int oO() const { return 2 * N + 4 * (N + 1); }
+  __device__ __forceinline__ float& U(int k, int i) const { return at(oU() + 2 * k + i); }
+  __device__ __forceinline__ float& X(int k, int i) const { return at(oX() + 4 * k + i); }
+  __device__ __forceinline__ float& O(int m, int i) const { return at(oO() + 4 * m + i); }
+  __device__ __forceinline__ void store_gains(int k, float k0, float k1, const float (&Kg)[2][6]) const {
+    uint32_t w[8];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) w[c] = pack_bf16x2(Kg[0][c], Kg[1][c]);
+    w[6] = pack_bf16x2(k0, k1);
+    w[7] = 0u;
+    __syncwarp();
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n"
+                 :: "r"(taddr + 8u * (uint32_t)k), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+  }
+  __device__ __forceinline__ void load_gains(int k, float& k0, float& k1, float (&Kr)[12]) const {
+    uint32_t w[8];
+    __syncwarp();
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                 : "r"(taddr + 8u * (uint32_t)k) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+    for (int c = 0; c < 6; ++c) { Kr[c] = bf_bits2f(w[c] & 0xFFFFu); Kr[6 + c] = bf_bits2f(w[c] >> 16); }
+    k0 = bf_bits2f(w[6] & 0xFFFFu); k1 = bf_bits2f(w[6] >> 16);
+  }
+  __device__ __forceinline__ void gains_fence() const {
+    __syncwarp();
+    asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+  }
+};
+MPC_HD int slots_per_problem_tmem(int N, int M) { return 2 * N + 4 * (N + 1) + 4 * M; }
+#endif
+
 MPC_HD int slots_per_problem(int N, int M, bool pack) { return 2 * N + 4 * (N + 1) + (pack ? 7 : 14) * N + 4 * M; }
 
 // ---- steering terms -------------------------------------------------------------------
@@ -691,6 +741,7 @@ MPC_PRAGMA_UNROLL_OBS
         P[sym6(i, jc)] = Qzz[sym6(i, jc)] + Kg[0][i] * Tm[0][jc] + Kg[1][i] * Tm[1][jc] +
                          Quz[0][i] * Kg[0][jc] + Quz[1][i] * Kg[1][jc];
   }
+  sl.gains_fence();
   *d1_out = d1;
   *d2_out = d2;
 }
@@ -701,10 +752,12 @@ MPC_PRAGMA_UNROLL_OBS
 // latency bound, so the second candidate is almost free and the gains are loaded once).
 // commit (NA == 1 only): overwrite (X, U) in place with the new trajectory.
 // with_cost = false skips the objective (the commit of an accepted trial already knows it).
+// open_loop = true ignores the stored policy (du = 0): the first rollout of a problem, whose gain slots
+// hold whatever the previous problem left there.
 // J[a] = objective, maxdu[a] = max |u_new - u_old| over the horizon.
 template <typename T, int NA, typename SL>
 MPC_HD void forward_pass(const SolverConfig& cfg, const ProblemScalars<T>& p, const RefTab<T>& ref,
-                         const SL& sl, const T* alpha, bool commit, bool with_cost, T* J, T* maxdu) {
+                         const SL& sl, const T* alpha, bool commit, bool with_cost, bool open_loop, T* J, T* maxdu) {
   const int N = cfg.N;
   const T dt = T(cfg.dt);
   T x[NA], y[NA], th[NA], v[NA], ap[NA], dp[NA], dap[NA], ddp[NA];
@@ -722,8 +775,9 @@ MPC_HD void forward_pass(const SolverConfig& cfg, const ProblemScalars<T>& p, co
 #pragma unroll
     for (int a = 0; a < NA; ++a) {
       const T ex = x[a] - xn, ey = y[a] - yn, eth = th[a] - thn, ev = v[a] - vn;
-      const T da = alpha[a] * f0 + Kr[0] * ex + Kr[1] * ey + Kr[2] * eth + Kr[3] * ev + Kr[4] * dap[a] + Kr[5] * ddp[a];
-      const T dd = alpha[a] * f1 + Kr[6] * ex + Kr[7] * ey + Kr[8] * eth + Kr[9] * ev + Kr[10] * dap[a] + Kr[11] * ddp[a];
+      T da = alpha[a] * f0 + Kr[0] * ex + Kr[1] * ey + Kr[2] * eth + Kr[3] * ev + Kr[4] * dap[a] + Kr[5] * ddp[a];
+      T dd = alpha[a] * f1 + Kr[6] * ex + Kr[7] * ey + Kr[8] * eth + Kr[9] * ev + Kr[10] * dap[a] + Kr[11] * ddp[a];
+      if (open_loop) { da = T(0); dd = T(0); }
       const Box<T> bx = control_box(th[a], v[a], dt);
       const T ac = clamp_(ua + da, bx.lo_a, bx.hi_a);
       T dc = ud + dd;
@@ -760,15 +814,13 @@ template <typename T> struct SolveState {
   bool done;
 };
 
-// Cold start (pure_mpc.py:244: zero controls).  The initial rollout is the commit pass under a zero
-// policy, so there is one rollout code path: solve_init, then forward_pass<T,1>(alpha = 1, commit),
+// Cold start (pure_mpc.py:244: zero controls).  The initial rollout is the commit pass in open-loop mode,
+// so there is one rollout code path: solve_init, then forward_pass<T,1>(commit, with_cost, open_loop),
 // then solve_init_finish with its objective.
 template <typename T, typename SL>
 MPC_HD void solve_init(const SolverConfig& cfg, const SL& sl, SolveState<T>& s) {
-  const T zero[2][6] = {{T(0), T(0), T(0), T(0), T(0), T(0)}, {T(0), T(0), T(0), T(0), T(0), T(0)}};
   for (int k = 0; k < cfg.N; ++k) {
     sl.U(k, 0) = T(0); sl.U(k, 1) = T(0);
-    sl.store_gains(k, T(0), T(0), zero);
     if (k > 0) { sl.X(k, 0) = T(0); sl.X(k, 1) = T(0); sl.X(k, 2) = T(0); sl.X(k, 3) = T(0); }   // 0 * stale memory could be NaN
   }
   s.mu = T(0); s.hs = T(1);
@@ -841,12 +893,12 @@ MPC_HD bool line_search_pass(const SolverConfig& cfg, const ProblemScalars<T>& p
                              const SL& sl, SolveState<T>& s, T d1, T d2, T& alpha, T& Jacc, T& mdacc) {
 #if MPC_LS_NA == 1
   T Jt, mt;
-  forward_pass<T, 1, SL>(cfg, p, ref, sl, &alpha, false, true, &Jt, &mt);
+  forward_pass<T, 1, SL>(cfg, p, ref, sl, &alpha, false, true, false, &Jt, &mt);
   s.trials += 1;
   if (accept_step(s.J, Jt, alpha * d1 + alpha * alpha * d2)) { Jacc = Jt; mdacc = mt; return true; }
 #else
   T al[2] = {alpha, alpha * T(MPC_LS_RATIO)}, Jt[2], mt[2];
-  forward_pass<T, 2, SL>(cfg, p, ref, sl, al, false, true, Jt, mt);
+  forward_pass<T, 2, SL>(cfg, p, ref, sl, al, false, true, false, Jt, mt);
   s.trials += 2;
   if (accept_step(s.J, Jt[0], al[0] * d1 + al[0] * al[0] * d2)) { alpha = al[0]; Jacc = Jt[0]; mdacc = mt[0]; return true; }
   if (accept_step(s.J, Jt[1], al[1] * d1 + al[1] * al[1] * d2)) { alpha = al[1]; Jacc = Jt[1]; mdacc = mt[1]; return true; }
@@ -863,7 +915,7 @@ MPC_HD void solve_one(const SolverConfig& cfg, const ProblemScalars<T>& p, const
   {
     solve_init(cfg, sl, s);
     T a1 = T(1), J0, md0;
-    forward_pass<T, 1, SL>(cfg, p, ref, sl, &a1, true, true, &J0, &md0);
+    forward_pass<T, 1, SL>(cfg, p, ref, sl, &a1, true, true, true, &J0, &md0);
     solve_init_finish(s, J0);
   }
   while (!s.done) {
@@ -874,7 +926,7 @@ MPC_HD void solve_one(const SolverConfig& cfg, const ProblemScalars<T>& p, const
     for (int t = 0; t < kLineSearchPasses && !acc; ++t) {
       acc = line_search_pass(cfg, p, ref, sl, s, d1, d2, alpha, Jn, md);
     }
-    if (acc) { T Jc, mdc; forward_pass<T, 1, SL>(cfg, p, ref, sl, &alpha, true, false, &Jc, &mdc); }
+    if (acc) { T Jc, mdc; forward_pass<T, 1, SL>(cfg, p, ref, sl, &alpha, true, false, false, &Jc, &mdc); }
 #if defined(MPC_TRACE) && !defined(__CUDA_ARCH__)
     printf("it %d J %.9g d1 %.4g d2 %.4g alpha %.4g acc %d Jn %.9g maxdu %.3g mu %.3g hs %g u0 %.6f %.6f\n", s.iter, (double)s.J,
            (double)d1, (double)d2, (double)alpha, (int)acc, (double)Jn, (double)md, (double)s.mu, (double)s.hs, (double)sl.U(0, 0), (double)sl.U(0, 1));

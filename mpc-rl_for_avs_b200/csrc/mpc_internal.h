@@ -54,6 +54,7 @@ struct SolveLaunch {
   int threads_per_block;
   int grid;
   size_t smem_bytes;
+  int use_tmem;           // gains in tensor memory (k_solve_tmem) instead of shared memory (k_solve)
 };
 cudaError_t configure_solve_kernel(size_t smem_bytes);
 cudaError_t launch_solve(const SolveLaunch& s, cudaStream_t stream);
@@ -62,5 +63,8 @@ cudaError_t launch_rollout_cost(const SolverConfig& cfg, const MpcProblemBatch& 
 cudaError_t upload_ref_table_solve();
 cudaError_t launch_fma_peak(float* sink, int iters, int grid, int block, cudaStream_t stream);
 size_t solve_smem_bytes(int N, int M, int tpb);
+size_t solve_smem_bytes_tmem(int N, int M, int tpb);
+bool tmem_layout_fits(int N, int tpb);
+cudaError_t launch_solve_tmem(const SolveLaunch& s, cudaStream_t stream);
 
 }  // namespace mpcb

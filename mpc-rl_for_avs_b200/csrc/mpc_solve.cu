@@ -137,7 +137,7 @@ k_solve(const SolverConfig cfg, const MpcProblemBatch batch, const MpcSolveOut o
     }
     if (active && (fresh || acc)) {      // commit sweep; only a fresh problem still needs its objective
       float Jc, mdc;
-      forward_pass<float, 1, SL>(cfg, p, ref, sl, &alpha, true, fresh, &Jc, &mdc);
+      forward_pass<float, 1, SL>(cfg, p, ref, sl, &alpha, true, fresh, fresh, &Jc, &mdc);
       if (fresh) Jn = Jc;
     }
     if (active) {
@@ -164,6 +164,141 @@ k_solve(const SolverConfig cfg, const MpcProblemBatch batch, const MpcSolveOut o
         }
       }
     }
+  }
+}
+
+// ---- variant with the gains in tensor memory -----------------------------------------------------
+// Same trip structure; differences forced by the warp-collective tcgen05.ld/st:
+//   * every sweep is executed by all 32 lanes whenever ANY lane needs it.  Lanes without work compute on
+//     whatever their slots hold (finite loops only, results discarded); their TMEM stores land in their own
+//     cells.  Under SIMT those lanes were waiting anyway.
+//   * shared memory per problem is 156 words -> 352 problems resident per SM (192 with gains in shared memory).
+constexpr int kTmemColsPerStage = 8;
+size_t solve_smem_bytes_tmem(int N, int M, int tpb) {
+  return (size_t)(kTabFloats + 4 + slots_per_problem_tmem(N, M) * tpb) * sizeof(float);
+}
+bool tmem_layout_fits(int N, int tpb) {
+  const int warps = tpb / 32, per_quarter = (warps + 3) / 4;
+  return kTmemColsPerStage * N * per_quarter <= 512;
+}
+
+template <int TPB>
+__global__ void __launch_bounds__(TPB, 1)
+k_solve_tmem(const SolverConfig cfg, const MpcProblemBatch batch, const MpcSolveOut out, const int B, int* __restrict__ work_counter,
+             const float* __restrict__ u_init) {
+  extern __shared__ __align__(16) float smem[];
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + kTabFloats);
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) {          // one warp allocates all 512 columns for the CTA (one CTA per SM)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n"
+                 :: "r"((uint32_t)__cvta_generic_to_shared(s_tmem)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  const RefTab<float> ref = stage_tables(smem);            // contains the __syncthreads()
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem_base = *s_tmem;
+  using SL = SlotsTmem<TPB>;
+  const SL sl{smem + kTabFloats + 4 + threadIdx.x,
+              tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(kTmemColsPerStage * cfg.N * (warp >> 2)), cfg.N, cfg.M};
+  const unsigned full = 0xffffffffu;
+
+  ProblemScalars<float> p;
+  p.x0 = 0.0; p.y0 = 0.0; p.ego_index = 0; p.n_obs = 0; p.is_collide = 0;
+  p.w_speed = 1.f; p.w_control = 1.f; p.w_diff = 1.f; p.vr_a = 0.f; p.vr_slope = 0.f; p.vr_b = 0.f; p.vr_n = 0;
+  SolveState<float> s;
+  s.J = 0.f; s.mu = 0.f; s.hs = 1.f; s.J_mark = 0.f; s.iter = 0; s.status = 0; s.trials = 0; s.fails = 0; s.done = true;
+  int idx = -1;
+  bool active = false, fresh = false, need_fetch = true;
+
+  for (;;) {
+    if (need_fetch) {
+      need_fetch = false;
+      idx = atomicAdd(work_counter, 1);
+      active = idx < B;
+      if (active) {
+        load_problem(batch, B, idx, cfg, p, sl);
+        solve_init(cfg, sl, s);
+        if (u_init) {
+#pragma unroll 1
+          for (int k = 0; k < cfg.N; ++k) {
+            sl.U(k, 0) = u_init[((size_t)idx * cfg.N + k) * 2];
+            sl.U(k, 1) = u_init[((size_t)idx * cfg.N + k) * 2 + 1];
+          }
+        }
+        fresh = true;
+      }
+    }
+    __syncwarp();
+    if (!__any_sync(full, active)) break;
+    float d1 = 0.f, d2 = 0.f, alpha = 1.f, Jn = 0.f, md = 0.f;
+    bool acc = false;
+    const bool run = active && !fresh;
+    if (__any_sync(full, run)) {                            // all 32 lanes sweep; only `run` lanes keep the result
+      backward_pass(cfg, p, ref, sl, s.mu, s.hs, &d1, &d2);
+      __syncwarp();
+      const bool ok = line_search_pass(cfg, p, ref, sl, s, d1, d2, alpha, Jn, md);
+      acc = run && ok;
+      __syncwarp();
+    }
+    const bool do_commit = active && (fresh || acc);
+    if (__any_sync(full, do_commit)) {
+      float Jc, mdc;
+      forward_pass<float, 1, SL>(cfg, p, ref, sl, &alpha, do_commit, fresh, fresh, &Jc, &mdc);
+      if (fresh) Jn = Jc;
+      __syncwarp();
+    }
+    if (active) {
+      if (fresh) {
+        solve_init_finish(s, Jn);
+        fresh = false;
+      } else {
+        after_line_search(cfg, s, acc, alpha, Jn, md);
+        if (s.done) {
+          if (!(s.J == s.J)) s.status |= kStatusNaN;
+          out.actions[2 * (size_t)idx] = sl.U(0, 0);
+          out.actions[2 * (size_t)idx + 1] = sl.U(0, 1);
+          if (out.status) out.status[idx] = s.status;
+          if (out.iters) out.iters[idx] = s.iter;
+          if (out.cost) out.cost[idx] = s.J;
+          if (out.U)
+#pragma unroll 1
+            for (int k = 0; k < cfg.N; ++k) {
+              out.U[((size_t)idx * cfg.N + k) * 2] = sl.U(k, 0);
+              out.U[((size_t)idx * cfg.N + k) * 2 + 1] = sl.U(k, 1);
+            }
+          active = false;
+          need_fetch = true;
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" :: "r"(tmem_base) : "memory");
+}
+
+template <int TPB> static cudaError_t launch_solve_tmem_t(const SolveLaunch& s, cudaStream_t stream) {
+  static size_t configured = 0;
+  if (s.smem_bytes > configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_solve_tmem<TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.smem_bytes);
+    if (e != cudaSuccess) return e;
+    configured = s.smem_bytes;
+  }
+  k_solve_tmem<TPB><<<s.grid, TPB, s.smem_bytes, stream>>>(s.cfg, s.batch, s.out, s.B, s.work_counter, s.u_init);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_solve_tmem(const SolveLaunch& s, cudaStream_t stream) {
+  switch (s.threads_per_block) {
+    case 128: return launch_solve_tmem_t<128>(s, stream);
+    case 192: return launch_solve_tmem_t<192>(s, stream);
+    case 256: return launch_solve_tmem_t<256>(s, stream);
+    case 288: return launch_solve_tmem_t<288>(s, stream);
+    case 320: return launch_solve_tmem_t<320>(s, stream);
+    case 352: return launch_solve_tmem_t<352>(s, stream);
+    case 384: return launch_solve_tmem_t<384>(s, stream);
+    default: return cudaErrorInvalidConfiguration;
   }
 }
 

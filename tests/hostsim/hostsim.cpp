@@ -155,7 +155,7 @@ extern "C" int hs_linesearch_probe(const SolverConfig* cfg, const double* ref, c
   for (int k = 0; k < cfg->N; ++k) { sl.U(k, 0) = U[2 * k]; sl.U(k, 1) = U[2 * k + 1]; }
   out[0] = rollout_nominal(*cfg, p, rt.tab(), sl, (double*)nullptr);
   backward_pass(*cfg, p, rt.tab(), sl, mu, 1.0, &out[1], &out[2]);
-  for (int a = 0; a < n_alpha; ++a) { double md, al = alphas[a]; forward_pass<double, 1>(*cfg, p, rt.tab(), sl, &al, false, true, &out[3 + a], &md); }
+  for (int a = 0; a < n_alpha; ++a) { double md, al = alphas[a]; forward_pass<double, 1>(*cfg, p, rt.tab(), sl, &al, false, true, false, &out[3 + a], &md); }
   for (int k = 0; k < cfg->N; ++k) { double f0, f1, Kr[12]; sl.load_gains(k, f0, f1, Kr); out[3 + n_alpha + 2 * k] = f0; out[3 + n_alpha + 2 * k + 1] = f1; }
   return 0;
 }
