@@ -239,9 +239,8 @@ def main() -> None:
         return
 
     # ---- roofline of the dominant kernel (k_solve), FP32 non-tensor ------------------------------------
-    sc = agent.solve_config()
-    tpb = sc["threads_small_batch"] if B < 500000 else sc["threads_large_batch"]
-    kernel_name = ("k_solve_tmem<%d>" if sc["gains_in_tmem"] else "k_solve<%d>") % tpb
+    sc = agent.solve_config(B)
+    kernel_name = ("k_solve_tmem<%d>" if sc["gains_in_tmem"] else "k_solve<%d>") % sc["threads_per_block"]
     peak_tf = agent.fp32_peak_tflops(5)
     solve_ms = kt["solve_ms"]
     alg_flops = flops_per_solve(mean_iters) * B - 18.7e3 * M * B      # collision-check flops belong to k_prepare
@@ -254,12 +253,13 @@ def main() -> None:
         pass
     traffic = None
     try:      # dram bytes read+written by k_solve per launch, from the committed `ncu --set full` capture of this command
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_k_solve_ncu_full.json")))["dram_traffic_bytes_per_launch"]
+        if B == 65536:       # the capture is of the default workload only
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_k_solve_ncu_full.json")))["dram_traffic_bytes_per_launch"]
     except Exception:  # noqa: BLE001
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     roofline = {"bound": "fp32", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
-                "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram__bytes_read+write; algorithmic %d)" % hbm_bytes, "kernel": "k_solve", "kernel_ms": solve_ms, "prepare_kernel_ms": kt["prepare_ms"],
+                "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram__bytes_read+write; algorithmic %d)" % hbm_bytes, "kernel": kernel_name, "kernel_ms": solve_ms, "prepare_kernel_ms": kt["prepare_ms"],
                 "kernel_share_of_step": (solve_ms * kt["n_solve"]) / ms if ms else None,
                 "peak_source": "FP32 FMA micro-kernel measured in this run (mpc_fp32_peak); MEASURED_PEAKS.json holds only HBM/bf16",
                 "alg_flops_per_launch": alg_flops, "mean_iters": mean_iters,
@@ -270,7 +270,7 @@ def main() -> None:
     # ---- cpu_baseline: the oracle port on the host cores, bounded sample of the same workload -----------
     cpu = None
     if not args.no_cpu_baseline:
-        cpu = cpu_baseline(args.cpu_seconds)
+        cpu = cpu_baseline(args.cpu_seconds, agent if world == 1 else None)
 
     line = {"metric": "mpc_solves_per_sec", "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -289,8 +289,10 @@ def main() -> None:
         dist.destroy_process_group()
 
 
-def cpu_baseline(seconds: float):
-    """Oracle port on all host cores, one problem per task, first problems of the seeded workload."""
+def cpu_baseline(seconds: float, agent=None):
+    """Oracle port on all host cores, one problem per task, first problems of the seeded workload.
+    With `agent`, the same problems also go through the CUDA path (untimed) and the line reports how
+    many first controls agree with the oracle's (the NLP is multi-modal from the cold start: DESIGN.md 6)."""
     import multiprocessing as mp
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import mpc_rl_for_avs_b200 as pkg
@@ -303,10 +305,22 @@ def cpu_baseline(seconds: float):
     with ctx.Pool(cores) as pool:
         pool.map(_ref_one, items[:cores], chunksize=1)
         t0 = time.perf_counter()
-        pool.map(_ref_one, items, chunksize=1)
+        ref_u0 = pool.map(_ref_one, items, chunksize=1)
         dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": "solves/s", "cores": cores, "kind": "port",
-            "sample": f"first {n} problems of the seed-1234 workload, one predict per task, {cores} processes, {dt:.1f} s"}
+    out = {"value": n / dt, "unit": "solves/s", "cores": cores, "kind": "port",
+           "sample": f"first {n} problems of the seed-1234 workload, one predict per task, {cores} processes, {dt:.1f} s"}
+    if agent is not None:
+        import numpy as np
+        act, status, _, _, _ = agent.predict_host(obs, np.where(has.reshape(-1), rs.reshape(-1), np.nan).astype(np.float32),
+                                                  reset_mask=np.ones(n, dtype=np.uint8))
+        du0 = np.abs(act.astype(np.float64) - np.asarray(ref_u0, dtype=np.float64).reshape(n, 2)).max(axis=1)
+        conv = status == 0
+        out["parity_sample"] = {"problems": n, "gpu_converged": int(conv.sum()),
+                                "first_control_within_1e-3": int((du0 < 1e-3).sum()),
+                                "first_control_within_1e-3_of_converged": int((du0[conv] < 1e-3).sum()),
+                                "note": "cold-start agreement; disagreements are other local optima (tests confirm each "
+                                        "converged GPU solution with the oracle warm-started from it)"}
+    return out
 
 
 if __name__ == "__main__":

@@ -184,9 +184,9 @@ MPC_API int mpc_fp32_peak(MpcHandle* h, int repeats, float* tflops_out);
  * mpc_timing_begin: CUDA events recorded on the launch stream around every launch */
 MPC_API int mpc_timing_begin(MpcHandle* h);
 MPC_API int mpc_timing_end(MpcHandle* h, float* prepare_ms_avg, float* solve_ms_avg, int* n_prepare, int* n_solve);
-/* which solve kernel the handle launches: *gains_in_tmem = 1 -> k_solve_tmem (gains in tensor memory), 0 -> k_solve
- * (gains in shared memory); block sizes used below / from 500k problems per launch */
-MPC_API int mpc_solve_config(const MpcHandle* h, int* gains_in_tmem, int* threads_small_batch, int* threads_large_batch);
+/* which solve kernel a launch of B problems uses: *gains_in_tmem = 1 -> k_solve_tmem (feedback gains in
+ * tensor memory), 0 -> k_solve (gains in shared memory); *threads_per_block = its block size (one block per SM) */
+MPC_API int mpc_solve_config(const MpcHandle* h, int B, int* gains_in_tmem, int* threads_per_block);
 /* device properties used for grid sizing */
 MPC_API int mpc_device_info(const MpcHandle* h, int* sm_count, int* cc_major, int* cc_minor, int* smem_per_block_optin);
 

@@ -106,7 +106,7 @@ def load() -> C.CDLL:
     lib.mpc_timing_begin.restype = C.c_int
     lib.mpc_timing_end.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.mpc_timing_end.restype = C.c_int
-    lib.mpc_solve_config.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.mpc_solve_config.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.mpc_solve_config.restype = C.c_int
     lib.mpc_device_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.mpc_device_info.restype = C.c_int

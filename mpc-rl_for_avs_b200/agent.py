@@ -356,10 +356,11 @@ class BatchedPureMPC:
         _capi.check(self._lib, self._h, self._lib.mpc_timing_end(self._h, C.byref(a), C.byref(b), C.byref(na), C.byref(nb)))
         return {"prepare_ms": float(a.value), "solve_ms": float(b.value), "n_prepare": na.value, "n_solve": nb.value}
 
-    def solve_config(self):
-        a, b, c = C.c_int(0), C.c_int(0), C.c_int(0)
-        _capi.check(self._lib, self._h, self._lib.mpc_solve_config(self._h, C.byref(a), C.byref(b), C.byref(c)))
-        return {"gains_in_tmem": bool(a.value), "threads_small_batch": b.value, "threads_large_batch": c.value}
+    def solve_config(self, B: int):
+        """Kernel and block size a launch of B problems uses (reporting only)."""
+        a, b = C.c_int(0), C.c_int(0)
+        _capi.check(self._lib, self._h, self._lib.mpc_solve_config(self._h, int(B), C.byref(a), C.byref(b)))
+        return {"gains_in_tmem": bool(a.value), "threads_per_block": b.value}
 
     def device_info(self):
         a, b, c, d = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)

@@ -202,14 +202,6 @@ MPC_API int mpc_create(const MpcConfig* cfg, int device, int max_batch, MpcHandl
   return MPC_OK;
 }
 
-MPC_API int mpc_solve_config(const MpcHandle* h, int* gains_in_tmem, int* threads_small_batch, int* threads_large_batch) {
-  if (!h) return MPC_ERR_BAD_ARG;
-  if (gains_in_tmem) *gains_in_tmem = h->use_tmem;
-  if (threads_small_batch) *threads_small_batch = (h->use_tmem && !h->tpb_forced) ? h->tpb_small : h->tpb;
-  if (threads_large_batch) *threads_large_batch = h->tpb;
-  return MPC_OK;
-}
-
 MPC_API int mpc_device_info(const MpcHandle* h, int* sm_count, int* cc_major, int* cc_minor, int* smem_per_block_optin) {
   if (!h) return MPC_ERR_BAD_ARG;
   if (sm_count) *sm_count = h->sm_count;
@@ -265,6 +257,40 @@ static int timed_end(MpcHandle* h, std::vector<cudaEvent_t>& v, cudaStream_t st)
   return MPC_OK;
 }
 
+// Block size and kernel of one launch.  The launch lasts as long as its slowest SM, and one solver
+// iteration takes longer the more warps share an SM's four schedulers, so: spread the batch over all SMs
+// first (one block per SM), and only then grow the block.  Both kernels run the same per-problem code and
+// store the gains in the same packed form, so the result of a problem does not depend on the choice
+// (tests/test_gpu_parity.py::test_result_independent_of_batch_size).
+static void pick_solve_launch(const MpcHandle* h, int B, SolveLaunch& s) {
+  s.threads_per_block = h->tpb; s.smem_bytes = h->smem; s.use_tmem = h->use_tmem;
+  if (h->tpb_forced) return;
+  const int N = h->scfg.N, M = h->scfg.M;
+  const int per_sm = (B + h->sm_count - 1) / h->sm_count;
+  int want = (per_sm + 31) / 32 * 32;
+  if (!h->use_tmem) {
+    if (want < h->tpb) { s.threads_per_block = want; s.smem_bytes = solve_smem_bytes(N, M, want); }
+    return;
+  }
+  if (B >= 500000) return;                                   // throughput bound: the largest block
+  if (want <= 96 && solve_smem_bytes(N, M, want) <= (size_t)h->smem_optin) {
+    s.use_tmem = 0; s.threads_per_block = want; s.smem_bytes = solve_smem_bytes(N, M, want);
+    return;
+  }
+  int tpb = want <= 128 ? 128 : (want <= 192 ? 192 : 256);
+  if (tpb > h->tpb_small) tpb = h->tpb_small;
+  s.threads_per_block = tpb; s.smem_bytes = solve_smem_bytes_tmem(N, M, tpb);
+}
+
+MPC_API int mpc_solve_config(const MpcHandle* h, int B, int* gains_in_tmem, int* threads_per_block) {
+  if (!h || B < 0) return MPC_ERR_BAD_ARG;
+  SolveLaunch s;
+  pick_solve_launch(h, B, s);
+  if (gains_in_tmem) *gains_in_tmem = s.use_tmem;
+  if (threads_per_block) *threads_per_block = s.threads_per_block;
+  return MPC_OK;
+}
+
 MPC_API int mpc_solve(MpcHandle* h, const MpcProblemBatch* batch, int B, const MpcSolveOut* out, void* stream) {
   int rc = check_batch(h, batch, B);
   if (rc) return rc;
@@ -276,12 +302,11 @@ MPC_API int mpc_solve(MpcHandle* h, const MpcProblemBatch* batch, int B, const M
   SolveLaunch s;
   s.cfg = h->scfg; s.batch = *batch; s.out = *out; s.B = B; s.work_counter = h->work_counter;
   s.u_init = h->u_init;
-  s.threads_per_block = h->tpb; s.smem_bytes = h->smem; s.use_tmem = h->use_tmem;
-  if (h->use_tmem && !h->tpb_forced && B < 500000) { s.threads_per_block = h->tpb_small; s.smem_bytes = h->smem_small; }
+  pick_solve_launch(h, B, s);
   int need = (B + s.threads_per_block - 1) / s.threads_per_block;
   s.grid = need < h->grid ? need : h->grid;
   if ((rc = timed_begin(h, h->ev_solve, st))) return rc;
-  CK(h, h->use_tmem ? launch_solve_tmem(s, st) : launch_solve(s, st));
+  CK(h, s.use_tmem ? launch_solve_tmem(s, st) : launch_solve(s, st));
   if ((rc = timed_end(h, h->ev_solve, st))) return rc;
   h->launches += 1;
   return MPC_OK;

@@ -310,6 +310,32 @@ def test_full_size_properties():
     assert np.array_equal(a3, a[:8].cpu().numpy())
 
 
+def test_result_independent_of_batch_size():
+    """The library picks kernel (gains in shared or tensor memory) and block size from the launch size;
+    a problem's result must not depend on that choice: bit-identical actions, status and iteration counts."""
+    pkg = _pkg()
+    M = 8
+    sizes = [65536, 40, 4096, 9000, 14000, 18000, 28000]
+    obs, rs, has = pkg.make_scenarios(max(sizes), M, seed=99)
+    rs_dev = torch.where(has.reshape(-1, 1), rs, torch.full_like(rs, float("nan"))).cuda()
+    obs_d = obs.cuda()
+    agent = pkg.BatchedPureMPC(CFG, vehicles_count=M + 1, max_batch=max(sizes), collision_check=True, weight_distance=10.0)
+    ref = None
+    seen = set()
+    for B in sizes:
+        agent.reset()
+        a = agent.predict_batch(obs_d[:B].contiguous(), ref_speed=rs_dev[:B].contiguous()).clone()
+        st, it = agent.status[:B].clone(), agent.iters[:B].clone()
+        sc = agent.solve_config(B)
+        seen.add((sc["gains_in_tmem"], sc["threads_per_block"]))
+        if ref is None:
+            ref = (a, st, it)
+            continue
+        assert torch.equal(a, ref[0][:B]), (B, sc)
+        assert torch.equal(st, ref[1][:B]) and torch.equal(it, ref[2][:B]), (B, sc)
+    assert len(seen) >= 4          # both kernels and several block sizes were exercised
+
+
 def test_edge_cases():
     pkg = _pkg()
     M = 8
