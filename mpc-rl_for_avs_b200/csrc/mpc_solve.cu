@@ -182,6 +182,10 @@ bool tmem_layout_fits(int N, int tpb) {
   return kTmemColsPerStage * N * per_quarter <= 512;
 }
 
+#ifndef MPC_BLOCK_SYNC
+#define MPC_BLOCK_SYNC 0
+#endif
+
 template <int TPB>
 __global__ void __launch_bounds__(TPB, 1)
 k_solve_tmem(const SolverConfig cfg, const MpcProblemBatch batch, const MpcSolveOut out, const int B, int* __restrict__ work_counter,
@@ -230,17 +234,30 @@ k_solve_tmem(const SolverConfig cfg, const MpcProblemBatch batch, const MpcSolve
       }
     }
     __syncwarp();
+#if MPC_BLOCK_SYNC >= 1
+    if (!__syncthreads_or(active)) break;
+#else
     if (!__any_sync(full, active)) break;
+#endif
     float d1 = 0.f, d2 = 0.f, alpha = 1.f, Jn = 0.f, md = 0.f;
     bool acc = false;
     const bool run = active && !fresh;
-    if (__any_sync(full, run)) {                            // all 32 lanes sweep; only `run` lanes keep the result
+    const bool any_run = __any_sync(full, run);
+    if (any_run) {                                          // all 32 lanes sweep; only `run` lanes keep the result
       backward_pass(cfg, p, ref, sl, s.mu, s.hs, &d1, &d2);
       __syncwarp();
+    }
+#if MPC_BLOCK_SYNC >= 2
+    __syncthreads();
+#endif
+    if (any_run) {
       const bool ok = line_search_pass(cfg, p, ref, sl, s, d1, d2, alpha, Jn, md);
       acc = run && ok;
       __syncwarp();
     }
+#if MPC_BLOCK_SYNC >= 3
+    __syncthreads();
+#endif
     const bool do_commit = active && (fresh || acc);
     if (__any_sync(full, do_commit)) {
       float Jc, mdc;
