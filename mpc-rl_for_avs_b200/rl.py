@@ -1,6 +1,6 @@
 """SURVEY 8-f "next" rows N1 + N2: a batched synthetic intersection environment and the batched
-A2C-MPC rollout / update loop (BASELINE config 4: 1024 vectorised envs, RL-set reference speed, MPC
-on the GPU).  NOT part of the hot path; plain PyTorch tensor code around `BatchedPureMPC`.
+A2C-MPC / PPO-MPC rollout and update loops (BASELINE config 4: 1024 vectorised envs, RL-set reference
+speed, MPC on the GPU).  NOT part of the hot path; plain PyTorch tensor code around `BatchedPureMPC`.
 
 What is mirrored from the reference (file:line in SaeedRahmani/MPC-RL_for_AVs):
   * rollout structure of `A2C_MPC.collect_rollouts` (agents/a2c_mpc.py:111-180): policy(obs) -> RL action =
@@ -149,54 +149,114 @@ class BatchedIntersectionEnv:
         reward = torch.where(arrived, torch.ones_like(reward), reward)
         truncated = self.t >= self.duration_steps
         done = crashed | arrived | truncated
-        info = {"crashed": crashed, "arrived": arrived, "truncated": truncated, "speed": v.clone()}
-        obs = self.reset(done) if bool(done.any()) else self.observe()
+        info = {"crashed": crashed, "arrived": arrived, "truncated": truncated & ~(crashed | arrived), "speed": v.clone()}
+        if bool(done.any()):
+            info["terminal_observation"] = self.observe()   # rows of finished envs: the state before the in-place reset
+            obs = self.reset(done)
+        else:
+            obs = self.observe()
         return obs, reward, done, info
 
 
-class ActorCritic(nn.Module):
-    """SB3 `MlpPolicy` shape for A2C: separate 64-64 tanh towers, state-independent log-std
-    (trainers/trainer_utils.py:6-26 builds the same policy with Box(-1, 1, (action_dim,)))."""
-
-    def __init__(self, obs_dim: int, action_dim: int = 1):
+class _MlpExtractor(nn.Module):
+    def __init__(self, obs_dim: int, width: int = 64):
         super().__init__()
-        self.pi = nn.Sequential(nn.Linear(obs_dim, 64), nn.Tanh(), nn.Linear(64, 64), nn.Tanh(), nn.Linear(64, action_dim))
-        self.vf = nn.Sequential(nn.Linear(obs_dim, 64), nn.Tanh(), nn.Linear(64, 64), nn.Tanh(), nn.Linear(64, 1))
-        self.log_std = nn.Parameter(torch.zeros(action_dim))
+        self.policy_net = nn.Sequential(nn.Linear(obs_dim, width), nn.Tanh(), nn.Linear(width, width), nn.Tanh())
+        self.value_net = nn.Sequential(nn.Linear(obs_dim, width), nn.Tanh(), nn.Linear(width, width), nn.Tanh())
+
+
+class ActorCritic(nn.Module):
+    """SB3 `MlpPolicy` as the reference builds it (trainers/trainer_utils.py:6-44: ActorCriticPolicy over
+    Box(-1, 1, (action_dim,))): separate 64-64 tanh towers, linear action / value heads.  Module and
+    parameter names are SB3's, so `state_dict()` is interchangeable with the `policy.pth` inside the
+    reference's zip checkpoints (weights/v0/*.zip; see checkpoint.py).
+
+    use_sde=False: state-independent log-std [action_dim] (A2C_MPC, cfg.yaml:43).
+    use_sde=True : generalised state-dependent exploration (PPO_MPC default, agents/ppo_mpc.py:114):
+                   log_std [64, action_dim]; noise = latent_pi @ theta with theta ~ N(0, exp(log_std)^2) drawn
+                   per environment by `reset_noise`; likelihood N(mean, sqrt(latent_pi^2 @ exp(log_std)^2))."""
+
+    def __init__(self, obs_dim: int, action_dim: int = 1, use_sde: bool = False, log_std_init: float = 0.0):
+        super().__init__()
+        self.use_sde, self.action_dim = bool(use_sde), int(action_dim)
+        self.mlp_extractor = _MlpExtractor(obs_dim)
+        self.action_net = nn.Linear(64, action_dim)
+        self.value_net = nn.Linear(64, 1)
+        shape = (64, action_dim) if use_sde else (action_dim,)
+        self.log_std = nn.Parameter(torch.full(shape, float(log_std_init)))
+        self._theta = None                                    # [B, 64, A] exploration matrices (gSDE)
+
+    def value(self, obs):
+        return self.value_net(self.mlp_extractor.value_net(obs)).squeeze(-1)
+
+    def reset_noise(self, n_envs: int) -> None:
+        if self.use_sde:
+            std = self.log_std.detach().exp()
+            self._theta = torch.randn(n_envs, *std.shape, device=std.device) * std
 
     def dist(self, obs):
-        return torch.distributions.Normal(self.pi(obs), self.log_std.exp())
+        latent = self.mlp_extractor.policy_net(obs)
+        mean = self.action_net(latent)
+        if self.use_sde:
+            var = (latent.detach() ** 2) @ (self.log_std.exp() ** 2)        # SB3: no gradient through the features
+            return torch.distributions.Normal(mean, torch.sqrt(var + 1e-6)), latent
+        return torch.distributions.Normal(mean, self.log_std.exp().expand_as(mean)), latent
 
-    def forward(self, obs):
-        d = self.dist(obs)
-        a = d.sample()
-        return a, self.vf(obs).squeeze(-1), d.log_prob(a).sum(-1)
+    def forward(self, obs, deterministic: bool = False):
+        d, latent = self.dist(obs)
+        if deterministic:
+            a = d.mean
+        elif self.use_sde:
+            if self._theta is None or self._theta.shape[0] != obs.shape[0]:
+                self.reset_noise(obs.shape[0])
+            a = d.mean + torch.bmm(latent.detach().unsqueeze(1), self._theta).squeeze(1)
+        else:
+            a = d.sample()
+        return a, self.value(obs), d.log_prob(a).sum(-1)
+
+    def evaluate_actions(self, obs, actions):
+        d, _ = self.dist(obs)
+        return self.value(obs), d.log_prob(actions).sum(-1), d.entropy().sum(-1)
 
 
-class A2CMPC:
-    """Batched counterpart of `A2C_MPC` v0 (agents/a2c_mpc.py): the policy's action is the MPC's reference speed."""
+class _MPCRollout:
+    """Rollout shared by the batched A2C-MPC and PPO-MPC: policy(obs) -> RL action -> MPC (reference speed in
+    version "v0", the three objective weights in "v1") -> env.step(raw (a, delta)); the buffer stores the RL
+    action (agents/a2c_mpc.py:111-180, agents/ppo_mpc.py:353-483).  Time-limit truncations bootstrap with the
+    value of the terminal observation as SB3 does (agents/ppo_mpc.py:451-461)."""
 
-    def __init__(self, env: BatchedIntersectionEnv, mpc, n_steps: int = 64, lr: float = 7e-4, gamma: float = 0.99,
-                 gae_lambda: float = 1.0, ent_coef: float = 0.0, vf_coef: float = 0.5, max_grad_norm: float = 0.5,
-                 rms_prop_eps: float = 1e-5, seed: int = 0):
-        self.env, self.mpc = env, mpc
+    clip_rl_action = False      # PPO_MPC clips the sample to the Box before the MPC sees it (agents/ppo_mpc.py:399-408);
+                                # A2C_MPC hands the raw Gaussian sample over (SURVEY quirk Q6)
+
+    def _setup(self, env, mpc, version, action_dim, n_steps, gamma, gae_lambda, use_sde, seed):
+        if version not in ("v0", "v1"):
+            raise ValueError("version must be 'v0' (RL sets the reference speed) or 'v1' (RL sets the MPC weights)")
+        self.env, self.mpc, self.version = env, mpc, version
         self.n_steps, self.gamma, self.lam = n_steps, gamma, gae_lambda
-        self.ent_coef, self.vf_coef, self.max_grad_norm = ent_coef, vf_coef, max_grad_norm
+        self.action_dim = action_dim if action_dim is not None else (1 if version == "v0" else 3)
         torch.manual_seed(seed)
-        self.policy = ActorCritic(env.V * 8, 1).to(env.device)
+        self.policy = ActorCritic(env.V * 8, self.action_dim, use_sde=use_sde).to(env.device)
         if dist.is_available() and dist.is_initialized():
             for p in self.policy.parameters():
                 dist.broadcast(p.data, 0)
-        self.opt = torch.optim.RMSprop(self.policy.parameters(), lr=lr, alpha=0.99, eps=rms_prop_eps)
         self.obs = env.observe()
         self.episode_start = torch.ones(env.B, dtype=torch.bool, device=env.device)
+        self.num_timesteps = 0
         self.stats = {"mpc_s": 0.0, "env_s": 0.0, "policy_s": 0.0, "update_s": 0.0, "steps": 0}
 
+    def mpc_action(self, obs, rl_action, reset_mask=None):
+        a = rl_action.clamp(-1.0, 1.0) if self.clip_rl_action else rl_action
+        if self.version == "v0":
+            return self.mpc.predict_batch(obs, ref_speed=a[:, :1].contiguous(), reset_mask=reset_mask)
+        return self.mpc.predict_batch(obs, weights=a[:, :3].contiguous(), reset_mask=reset_mask)
+
     def collect_rollouts(self):
-        B, T, dev = self.env.B, self.n_steps, self.env.device
-        buf = {k: torch.zeros(T, B, device=dev) for k in ("act", "rew", "val", "logp", "done")}
+        B, T, dev, A = self.env.B, self.n_steps, self.env.device, self.action_dim
+        buf = {k: torch.zeros(T, B, device=dev) for k in ("rew", "val", "logp", "done")}
+        buf["act"] = torch.zeros(T, B, A, device=dev)
         obs_buf = torch.zeros(T, B, self.env.V * 8, device=dev)
         cuda = dev.type == "cuda"
+        self.policy.reset_noise(B)                          # sde_sample_freq = -1: once per rollout
         for t in range(T):
             t0 = time.perf_counter()
             with torch.no_grad():
@@ -205,24 +265,29 @@ class A2CMPC:
             if cuda:
                 torch.cuda.synchronize(dev)
             t1 = time.perf_counter()
-            # v0: RL action = reference speed (agents/a2c_mpc.py:138-150); the latch of finished envs is cleared
-            mpc_action = self.mpc.predict_batch(self.obs, ref_speed=a, reset_mask=self.episode_start)
+            mpc_action = self.mpc_action(self.obs, a, self.episode_start)   # the latch of finished envs is cleared
             if cuda:
                 torch.cuda.synchronize(dev)
             t2 = time.perf_counter()
-            new_obs, rew, done, _ = self.env.step(mpc_action)
+            new_obs, rew, done, info = self.env.step(mpc_action)
+            trunc = info["truncated"]
+            if bool(trunc.any()):
+                with torch.no_grad():
+                    tv = self.policy.value(info["terminal_observation"].reshape(B, -1))
+                rew = rew + self.gamma * tv * trunc.float()
             if cuda:
                 torch.cuda.synchronize(dev)
             t3 = time.perf_counter()
-            obs_buf[t], buf["act"][t], buf["rew"][t], buf["val"][t], buf["logp"][t] = flat, a.squeeze(-1), rew, v, lp
+            obs_buf[t], buf["act"][t], buf["rew"][t], buf["val"][t], buf["logp"][t] = flat, a, rew, v, lp
             buf["done"][t] = done.float()
             self.obs, self.episode_start = new_obs, done
             self.stats["policy_s"] += t1 - t0
             self.stats["mpc_s"] += t2 - t1
             self.stats["env_s"] += t3 - t2
             self.stats["steps"] += B
+        self.num_timesteps += B * T
         with torch.no_grad():
-            last_v = self.policy.vf(self.obs.reshape(B, -1)).squeeze(-1)
+            last_v = self.policy.value(self.obs.reshape(B, -1))
         adv = torch.zeros(T, B, device=dev)
         gae = torch.zeros(B, device=dev)
         for t in reversed(range(T)):                        # SB3 RolloutBuffer.compute_returns_and_advantage
@@ -233,28 +298,115 @@ class A2CMPC:
             adv[t] = gae
         return obs_buf, buf, adv, adv + buf["val"]
 
-    def train_step(self) -> Dict[str, float]:
-        obs_buf, buf, adv, ret = self.collect_rollouts()
-        t0 = time.perf_counter()
-        flat = obs_buf.reshape(-1, obs_buf.shape[-1])
-        d = self.policy.dist(flat)
-        logp = d.log_prob(buf["act"].reshape(-1, 1)).sum(-1)
-        values = self.policy.vf(flat).squeeze(-1)
-        policy_loss = -(adv.reshape(-1) * logp).mean()
-        value_loss = torch.nn.functional.mse_loss(ret.reshape(-1), values)
-        entropy_loss = -d.entropy().sum(-1).mean()
-        loss = policy_loss + self.ent_coef * entropy_loss + self.vf_coef * value_loss
+    def _step_optimizer(self, loss):
         self.opt.zero_grad()
         loss.backward()
         if dist.is_available() and dist.is_initialized():   # data-parallel update over the env shards
             w = dist.get_world_size()
             for p in self.policy.parameters():
-                dist.all_reduce(p.grad)
-                p.grad /= w
+                if p.grad is not None:
+                    dist.all_reduce(p.grad)
+                    p.grad /= w
         nn.utils.clip_grad_norm_(self.policy.parameters(), self.max_grad_norm)
         self.opt.step()
+
+    @torch.no_grad()
+    def predict(self, obs, deterministic: bool = True):
+        """Inference as `BaseTrainer.predict` does it (trainers/trainer.py:345-373): policy -> MPC -> (a, delta)."""
+        a, _, _ = self.policy(obs.reshape(obs.shape[0], -1), deterministic=deterministic)
+        return self.mpc_action(obs, a)
+
+
+class A2CMPC(_MPCRollout):
+    """Batched counterpart of `A2C_MPC` (agents/a2c_mpc.py) with the hyper-parameters of cfg.yaml:30-45."""
+
+    def __init__(self, env: BatchedIntersectionEnv, mpc, n_steps: int = 64, lr: float = 7e-4, gamma: float = 0.99,
+                 gae_lambda: float = 1.0, ent_coef: float = 0.0, vf_coef: float = 0.5, max_grad_norm: float = 0.5,
+                 rms_prop_eps: float = 1e-5, seed: int = 0, version: str = "v0", action_dim: Optional[int] = None,
+                 use_sde: bool = False):
+        self._setup(env, mpc, version, action_dim, n_steps, gamma, gae_lambda, use_sde, seed)
+        self.ent_coef, self.vf_coef, self.max_grad_norm = ent_coef, vf_coef, max_grad_norm
+        self.opt = torch.optim.RMSprop(self.policy.parameters(), lr=lr, alpha=0.99, eps=rms_prop_eps)
+
+    def train_step(self) -> Dict[str, float]:
+        obs_buf, buf, adv, ret = self.collect_rollouts()
+        t0 = time.perf_counter()
+        flat = obs_buf.reshape(-1, obs_buf.shape[-1])
+        values, logp, entropy = self.policy.evaluate_actions(flat, buf["act"].reshape(-1, self.action_dim))
+        policy_loss = -(adv.reshape(-1) * logp).mean()      # agents/a2c_mpc.py:182-226 (normalize_advantage false)
+        value_loss = torch.nn.functional.mse_loss(ret.reshape(-1), values)
+        entropy_loss = -entropy.mean()
+        loss = policy_loss + self.ent_coef * entropy_loss + self.vf_coef * value_loss
+        self._step_optimizer(loss)
         if self.env.device.type == "cuda":
             torch.cuda.synchronize(self.env.device)
         self.stats["update_s"] += time.perf_counter() - t0
         return {"loss": float(loss.detach()), "policy_loss": float(policy_loss.detach()), "value_loss": float(value_loss.detach()),
                 "mean_reward": float(buf["rew"].mean()), "done_rate": float(buf["done"].mean())}
+
+
+class PPOMPC(_MPCRollout):
+    """Batched counterpart of `PPO_MPC` (agents/ppo_mpc.py): clipped-surrogate PPO around the MPC, gSDE on by
+    default (agents/ppo_mpc.py:114), hyper-parameters of cfg.yaml:62-87 (lr 3e-4, 10 epochs, clip 0.2,
+    GAE 0.95, advantages normalised per minibatch, vf_coef 0.5, max_grad_norm 0.5, Adam).  `batch_size` is the
+    minibatch size of the update (agents/ppo_mpc.py:213-333); with B environments a rollout holds
+    B * n_steps samples, so the default scales the reference's 256 by the number of environments."""
+
+    clip_rl_action = True
+
+    def __init__(self, env: BatchedIntersectionEnv, mpc, n_steps: int = 256, batch_size: Optional[int] = None,
+                 n_epochs: int = 10, lr: float = 3e-4, gamma: float = 0.99, gae_lambda: float = 0.95,
+                 clip_range: float = 0.2, clip_range_vf: Optional[float] = None, normalize_advantage: bool = True,
+                 ent_coef: float = 0.0, vf_coef: float = 0.5, max_grad_norm: float = 0.5, target_kl: Optional[float] = None,
+                 use_sde: bool = True, seed: int = 0, version: str = "v0", action_dim: Optional[int] = None):
+        self._setup(env, mpc, version, action_dim, n_steps, gamma, gae_lambda, use_sde, seed)
+        self.batch_size = batch_size if batch_size is not None else 256 * env.B
+        self.n_epochs, self.clip_range, self.clip_range_vf = n_epochs, clip_range, clip_range_vf
+        self.normalize_advantage, self.target_kl = normalize_advantage, target_kl
+        self.ent_coef, self.vf_coef, self.max_grad_norm = ent_coef, vf_coef, max_grad_norm
+        self.opt = torch.optim.Adam(self.policy.parameters(), lr=lr, eps=1e-5)
+        self.gen = torch.Generator(device=env.device)
+        self.gen.manual_seed(seed + 1)
+
+    def train_step(self) -> Dict[str, float]:
+        obs_buf, buf, adv, ret = self.collect_rollouts()
+        t0 = time.perf_counter()
+        n = obs_buf.shape[0] * obs_buf.shape[1]
+        obs_f, act_f = obs_buf.reshape(n, -1), buf["act"].reshape(n, self.action_dim)
+        adv_f, ret_f, val_f, logp_f = adv.reshape(n), ret.reshape(n), buf["val"].reshape(n), buf["logp"].reshape(n)
+        bs = min(self.batch_size, n)
+        last = {}
+        stop = False
+        for _ in range(self.n_epochs):
+            perm = torch.randperm(n, device=obs_f.device, generator=self.gen)
+            for lo in range(0, n, bs):
+                idx = perm[lo:lo + bs]
+                if self.policy.use_sde:
+                    self.policy.reset_noise(idx.shape[0])
+                values, logp, entropy = self.policy.evaluate_actions(obs_f[idx], act_f[idx])
+                a = adv_f[idx]
+                if self.normalize_advantage and a.numel() > 1:
+                    a = (a - a.mean()) / (a.std() + 1e-8)
+                ratio = torch.exp(logp - logp_f[idx])
+                policy_loss = -torch.min(a * ratio, a * ratio.clamp(1 - self.clip_range, 1 + self.clip_range)).mean()
+                vp = values if self.clip_range_vf is None else val_f[idx] + (values - val_f[idx]).clamp(-self.clip_range_vf, self.clip_range_vf)
+                value_loss = torch.nn.functional.mse_loss(ret_f[idx], vp)
+                entropy_loss = -entropy.mean()
+                loss = policy_loss + self.ent_coef * entropy_loss + self.vf_coef * value_loss
+                with torch.no_grad():
+                    log_ratio = logp - logp_f[idx]
+                    approx_kl = float(((log_ratio.exp() - 1) - log_ratio).mean())
+                    clip_frac = float(((ratio - 1).abs() > self.clip_range).float().mean())
+                if self.target_kl is not None and approx_kl > 1.5 * self.target_kl:
+                    stop = True
+                    break
+                self._step_optimizer(loss)
+                last = {"loss": float(loss.detach()), "policy_loss": float(policy_loss.detach()),
+                        "value_loss": float(value_loss.detach()), "approx_kl": approx_kl, "clip_fraction": clip_frac}
+            if stop:
+                break
+        if self.env.device.type == "cuda":
+            torch.cuda.synchronize(self.env.device)
+        self.stats["update_s"] += time.perf_counter() - t0
+        last.update({"mean_reward": float(buf["rew"].mean()), "done_rate": float(buf["done"].mean())})
+        return last

@@ -56,6 +56,87 @@ def test_a2c_plumbing_cpu():
     assert algo.stats["steps"] == 40
 
 
+def test_ppo_plumbing_cpu():
+    from mpc_rl_for_avs_b200.rl import PPOMPC, BatchedIntersectionEnv
+    for version, use_sde in (("v0", True), ("v1", False)):
+        env = BatchedIntersectionEnv(8, 9, device="cpu", seed=2, duration_steps=4)     # truncations -> value bootstrap path
+        algo = PPOMPC(env, _StubMPC(), n_steps=6, n_epochs=2, batch_size=16, use_sde=use_sde, version=version)
+        assert algo.policy.log_std.shape == ((64, algo.action_dim) if use_sde else (algo.action_dim,))
+        assert algo.action_dim == (1 if version == "v0" else 3)
+        p0 = [p.detach().clone() for p in algo.policy.parameters()]
+        log = algo.train_step()
+        assert all(np.isfinite(v) for v in log.values()) and "approx_kl" in log
+        assert any(not torch.equal(a, b) for a, b in zip(p0, algo.policy.parameters()))
+        assert algo.num_timesteps == 48
+        # PPO_MPC clips the RL action to the Box before the MPC; A2C_MPC does not (quirk Q6)
+        seen = {}
+
+        class Spy(_StubMPC):
+            def predict_batch(self, obs, ref_speed=None, weights=None, reset_mask=None):
+                seen["rs"], seen["w"] = ref_speed, weights
+                return super().predict_batch(obs)
+        algo.mpc = Spy()
+        algo.mpc_action(env.observe(), torch.full((8, algo.action_dim), 7.0))
+        got = seen["rs"] if version == "v0" else seen["w"]
+        assert float(got.max()) == 1.0 and got.shape == (8, 1 if version == "v0" else 3)
+
+
+def test_gsde_likelihood_matches_sampling_cpu():
+    """gSDE: noise = latent @ theta, theta ~ N(0, sigma^2) per env; the per-sample std is sqrt(latent^2 @ sigma^2)."""
+    from mpc_rl_for_avs_b200.rl import ActorCritic
+    torch.manual_seed(0)
+    pol = ActorCritic(80, 1, use_sde=True, log_std_init=-1.0)
+    obs = torch.randn(1, 80).repeat(20000, 1)
+    pol.reset_noise(20000)
+    a, _, lp = pol(obs)
+    d, _ = pol.dist(obs)
+    assert abs(float(a.std()) / float(d.stddev[0]) - 1.0) < 0.03 and abs(float(a.mean() - d.mean[0])) < 0.02
+    # same exploration matrix -> same action for the same observation until the next reset_noise
+    a2, _, _ = pol(obs)
+    assert torch.equal(a, a2)
+    v, lp2, ent = pol.evaluate_actions(obs, a)
+    assert torch.allclose(lp, lp2)
+
+
+def test_sb3_zip_checkpoints_cpu(tmp_path):
+    import os
+    from mpc_rl_for_avs_b200 import checkpoint
+    from mpc_rl_for_avs_b200.rl import ActorCritic
+    torch.manual_seed(1)
+    for use_sde in (False, True):
+        pol = ActorCritic(80, 1, use_sde=use_sde)
+        path = str(tmp_path / f"p{int(use_sde)}.zip")
+        checkpoint.save_sb3_policy(path, pol, {"n_steps": 64, "gamma": 0.99})
+        pol2, data = checkpoint.load_sb3_policy(path)
+        assert pol2.use_sde == use_sde and data["n_steps"] == 64
+        x = torch.randn(5, 80)
+        assert torch.equal(pol(x, deterministic=True)[0], pol2(x, deterministic=True)[0])
+    # the reference's own checkpoints (A2C: state-independent std; PPO: gSDE), when the reference tree is present
+    ref = "/root/reference/weights/v0"
+    if os.path.isdir(ref):
+        for name, sde in (("test_a2c_v0.zip", False), ("test_ppo_v0.zip", True)):
+            pol, data = checkpoint.load_sb3_policy(os.path.join(ref, name))
+            assert pol.use_sde == sde and data["observation_space_shape"] == (10, 8) and data["action_space_shape"] == (1,)
+            a, v, lp = pol(torch.zeros(3, 80), deterministic=True)
+            assert a.shape == (3, 1) and torch.isfinite(a).all() and torch.isfinite(v).all()
+
+
+def test_evaluation_harness_cpu():
+    from mpc_rl_for_avs_b200 import evaluation
+    from mpc_rl_for_avs_b200.rl import A2CMPC, BatchedIntersectionEnv
+    make_env = lambda: BatchedIntersectionEnv(16, 9, device="cpu", seed=11, duration_steps=40)   # noqa: E731
+    stub = _StubMPC()
+    algo = A2CMPC(make_env(), stub, n_steps=2)
+    res = evaluation.compare({"pure_mpc": evaluation.pure_mpc_controller(stub),
+                              "mpcrl": evaluation.mpcrl_controller(algo)}, make_env, n_episodes=40, max_steps=30)
+    for r in res.values():
+        assert r["episodes"] == 40 and 0 <= r["success_rate"] <= 1 and 0 <= r["collision_rate"] <= 1
+        assert 1 <= r["avg_steps"] <= 30 and abs(r["avg_time"] - r["avg_steps"] * 0.1) < 1e-6 and r["avg_speed"] > 0
+    # same seeds -> same numbers
+    again = evaluation.evaluate(evaluation.pure_mpc_controller(stub), make_env(), 40, 30)
+    assert again == res["pure_mpc"]
+
+
 @pytest.mark.gpu
 def test_a2c_mpc_in_the_loop_gpu():
     import mpc_rl_for_avs_b200 as pkg
@@ -71,3 +152,22 @@ def test_a2c_mpc_in_the_loop_gpu():
     assert algo.stats["steps"] == 2 * 8 * B and algo.stats["mpc_s"] > 0
     # the latch of finished environments was cleared through reset_mask
     assert int(mpc.collision_memory[:B].max()) <= 10
+
+
+@pytest.mark.gpu
+def test_ppo_mpc_and_evaluation_gpu():
+    import mpc_rl_for_avs_b200 as pkg
+    from mpc_rl_for_avs_b200 import evaluation
+    from mpc_rl_for_avs_b200.rl import PPOMPC, BatchedIntersectionEnv
+    B = 256
+    cfg = {"horizon": 16, "weight_speed": 1, "weight_control": 1, "weight_input_diff": 1}
+    mpc = pkg.BatchedPureMPC(cfg, vehicles_count=10, max_batch=B, collision_check=True)
+    algo = PPOMPC(BatchedIntersectionEnv(B, 9, device="cuda", seed=5), mpc, n_steps=8, n_epochs=2, batch_size=512)
+    log = algo.train_step()
+    assert all(np.isfinite(v) for v in log.values())
+    make_env = lambda: BatchedIntersectionEnv(B, 9, device="cuda", seed=6, duration_steps=150)   # noqa: E731
+    res = evaluation.compare({"pure_mpc": evaluation.pure_mpc_controller(mpc), "mpcrl": evaluation.mpcrl_controller(algo)},
+                             make_env, n_episodes=B, max_steps=150)
+    assert res["pure_mpc"]["episodes"] == B and res["mpcrl"]["episodes"] == B
+    # the collision-aware MPC on the raw action path drives: it moves and most episodes end without a crash
+    assert res["pure_mpc"]["avg_speed"] > 1.0 and res["pure_mpc"]["collision_rate"] < 0.6
