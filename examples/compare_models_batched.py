@@ -34,7 +34,7 @@ def main():
     mpc_rl = pkg.BatchedPureMPC(cfg, vehicles_count=V, max_batch=args.envs, collision_check=True)
     algo = A2CMPC(make_env(), mpc_rl, n_steps=1)
     if args.policy:
-        checkpoint.load_sb3_policy(args.policy, device="cuda", policy=algo.policy)
+        algo.policy, _ = checkpoint.load_sb3_policy(args.policy, device="cuda")     # gSDE or plain, as saved
     res = evaluation.compare({"pure_mpc": evaluation.pure_mpc_controller(mpc),
                               "pure_mpc_no_collision": evaluation.pure_mpc_controller(mpc_nc),
                               "mpcrl": evaluation.mpcrl_controller(algo)}, make_env, args.episodes, args.steps)

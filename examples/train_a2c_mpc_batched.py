@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--warm-start", action="store_true")
     ap.add_argument("--algo", choices=("a2c", "ppo"), default="a2c")
     ap.add_argument("--save", default="", help="write the policy as an SB3-layout zip")
+    ap.add_argument("--eager", action="store_true", help="no CUDA graph: per-phase shares are measured instead")
     args = ap.parse_args()
     world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -40,7 +41,8 @@ def main():
     env = BatchedIntersectionEnv(args.envs, n_others, device=f"cuda:{local}", seed=1234 + rank)
     cfg = {"horizon": args.horizon, "weight_speed": 1, "weight_control": 1, "weight_input_diff": 1}
     mpc = pkg.BatchedPureMPC(cfg, vehicles_count=n_others + 1, max_batch=args.envs, device=local, collision_check=True)
-    algo = A2CMPC(env, mpc, n_steps=args.n_steps) if args.algo == "a2c" else PPOMPC(env, mpc, n_steps=args.n_steps)
+    Algo = A2CMPC if args.algo == "a2c" else PPOMPC
+    algo = Algo(env, mpc, n_steps=args.n_steps, graph=not args.eager)
     algo.train_step()                                          # warm-up (allocator, first launches)
     for k in algo.stats:
         algo.stats[k] = 0
@@ -51,8 +53,9 @@ def main():
     if rank == 0:
         print(json.dumps({"metric": f"{args.algo}_mpc_env_steps_per_sec", "value": world * s["steps"] / wall, "n_gpus": world,
                           "envs_per_gpu": args.envs, "n_steps": args.n_steps, "updates": args.updates, "horizon": args.horizon,
-                          "share": {k: s[k] / wall for k in ("policy_s", "mpc_s", "env_s", "update_s")},
-                          "mpc_solves_per_sec_in_loop": s["steps"] / s["mpc_s"], "last": logs[-1],
+                          "mode": "eager (per-phase sync)" if args.eager else "CUDA graph per transition",
+                          "share": {k: s[k] / wall for k in (("policy_s", "mpc_s", "env_s", "update_s") if args.eager else ("rollout_s", "update_s"))},
+                          "mpc_solves_per_sec_in_loop": (s["steps"] / s["mpc_s"]) if args.eager else None, "last": logs[-1],
                           "data": "synthetic stand-in env (mpc_rl_for_avs_b200.rl)"}))
     if rank == 0 and args.save:
         checkpoint.save_sb3_policy(args.save, algo.policy, {"n_steps": args.n_steps, "num_timesteps": algo.num_timesteps,

@@ -34,15 +34,26 @@ from .scenarios import reference_path
 _LANE_HEADING = (-math.pi / 2, 0.0, math.pi / 2, math.pi)
 
 
+def _i64(x: int) -> int:
+    """Python int -> the same 64-bit pattern as a signed value (torch int64 arithmetic wraps)."""
+    x &= (1 << 64) - 1
+    return x - (1 << 64) if x >= (1 << 63) else x
+
+
 class BatchedIntersectionEnv:
-    """B independent intersection scenes as tensors on one device (CPU works too: used by the CPU tests)."""
+    """B independent intersection scenes as tensors on one device (CPU works too: used by the CPU tests).
+
+    `step` / `reset(mask)` / `observe` are fixed-shape tensor programs without any host synchronisation
+    (no `.any()` / `.item()` branches, masked updates instead), and the random draws come from a counter-based
+    generator kept on the device (splitmix64 over (seed, draw counter, env, slot)), so a whole
+    policy -> MPC -> env transition can be captured in a CUDA graph (`_MPCRollout(graph=True)`)."""
 
     def __init__(self, n_envs: int, n_others: int = 9, device="cuda", seed: int = 0, policy_frequency: int = 10,
                  simulation_frequency: int = 30, duration_steps: int = 100, action_scaling: str = "sb3_raw"):
+        if action_scaling not in ("sb3_raw", "physical"):
+            raise ValueError("action_scaling must be 'sb3_raw' or 'physical'")
         self.B, self.M, self.V = int(n_envs), int(n_others), int(n_others) + 1
         self.device = torch.device(device)
-        self.gen = torch.Generator(device=self.device)
-        self.gen.manual_seed(seed)
         self.sub = simulation_frequency // policy_frequency
         self.dt_sim = 1.0 / simulation_frequency
         self.duration_steps = duration_steps
@@ -54,41 +65,54 @@ class BatchedIntersectionEnv:
         self.oth = torch.zeros(self.B, self.M, 4, **f)       # x, y, speed, heading
         self.t = torch.zeros(self.B, dtype=torch.int32, device=self.device)
         self.crashed = torch.zeros(self.B, dtype=torch.bool, device=self.device)
+        self._lane_heading = torch.tensor(_LANE_HEADING, **f)
+        self._ctr = torch.full((1,), _i64(0x9E3779B97F4A7C15 * (2 * int(seed) + 1)), dtype=torch.int64, device=self.device)
+        self._slot = torch.arange(self.B * 64, dtype=torch.int64, device=self.device).reshape(self.B, 64)
         self.reset()
 
-    # ----------------------------------------------------------------------------------------------
-    def _rand(self, *shape):
-        return torch.rand(*shape, generator=self.gen, device=self.device)
+    # ---------------------------------------------------------------------------------------------- random draws
+    def _rand(self, n: int) -> torch.Tensor:
+        """[B, n] uniforms in (0, 1): splitmix64 of (draw counter, env * 64 + column); n <= 64."""
+        self._ctr += _i64(0xD1B54A32D192ED03)
+        x = self._slot[:, :n] * _i64(0x9E3779B97F4A7C15) + self._ctr
+        x = (x ^ ((x >> 30) & ((1 << 34) - 1))) * _i64(0xBF58476D1CE4E5B9)
+        x = (x ^ ((x >> 27) & ((1 << 37) - 1))) * _i64(0x94D049BB133111EB)
+        x = x ^ ((x >> 31) & ((1 << 33) - 1))
+        return (((x >> 40) & ((1 << 24) - 1)).float() + 0.5) * (1.0 / (1 << 24))
 
-    def _randn(self, *shape):
-        return torch.randn(*shape, generator=self.gen, device=self.device)
+    def _randn(self, n: int) -> torch.Tensor:
+        u = self._rand(2 * n)
+        return torch.sqrt(-2.0 * torch.log(u[:, :n])) * torch.cos((2.0 * math.pi) * u[:, n:])
 
-    def _spawn_others(self, n: int) -> torch.Tensor:
-        c = torch.randint(0, 4, (n, self.M), generator=self.gen, device=self.device)
-        lane = 2.0 + 0.2 * self._randn(n, self.M)
-        d = -30.0 + 100.0 * self._rand(n, self.M)
-        ang = c.float() * (math.pi / 2)
+    def _spawn_others(self) -> torch.Tensor:
+        """[B, M, 4] fresh vehicles on the four approach lanes (envs/intersection_env__.py:164-170, :409-416)."""
+        M = self.M
+        c = torch.clamp((self._rand(M) * 4.0).floor(), max=3.0)
+        lane = 2.0 + 0.2 * self._randn(M)
+        d = -30.0 + 100.0 * self._rand(M)
+        ang = c * (math.pi / 2)
         px = torch.cos(ang) * lane - torch.sin(ang) * d
         py = torch.sin(ang) * lane + torch.cos(ang) * d
-        spd = torch.clamp(8.0 + self._randn(n, self.M), min=0.5)
-        hd = torch.tensor(_LANE_HEADING, device=self.device)[c]
+        spd = torch.clamp(8.0 + self._randn(M), min=0.5)
+        hd = self._lane_heading[c.long()]
         return torch.stack([px, py, spd, hd], dim=-1)
 
     def reset(self, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
         m = torch.ones(self.B, dtype=torch.bool, device=self.device) if mask is None else mask.to(self.device).bool()
-        n = int(m.sum())
-        if n:
-            ego = torch.zeros(n, 4, device=self.device)
-            ego[:, 0] = 2.0 + 0.1 * self._randn(n)
-            ego[:, 1] = 50.0 + self._rand(n)                 # envs/intersection_env__.py:303-315: spawns at the south entry
-            ego[:, 2] = -math.pi / 2
-            ego[:, 3] = 8.0 + 2.0 * self._rand(n)
-            oth = self._spawn_others(n)
-            near = torch.hypot(oth[..., 0] - ego[:, None, 0], oth[..., 1] - ego[:, None, 1]) < 8.0
-            oth[..., 1] = torch.where(near & (oth[..., 3] == -math.pi / 2), oth[..., 1] - 20.0, oth[..., 1])
-            self.ego[m], self.oth[m] = ego, oth
-            self.t[m] = 0
-            self.crashed[m] = False
+        r = self._rand(2)
+        ego = torch.stack([2.0 + 0.1 * self._randn(1)[:, 0],
+                           50.0 + r[:, 0],                   # envs/intersection_env__.py:303-315: spawns at the south entry
+                           torch.full((self.B,), -math.pi / 2, device=self.device),
+                           8.0 + 2.0 * r[:, 1]], dim=1)
+        oth = self._spawn_others()
+        near = torch.hypot(oth[..., 0] - ego[:, None, 0], oth[..., 1] - ego[:, None, 1]) < 8.0
+        oy = torch.where(near & (oth[..., 3] == -math.pi / 2), oth[..., 1] - 20.0, oth[..., 1])
+        oth = torch.stack([oth[..., 0], oy, oth[..., 2], oth[..., 3]], dim=-1)
+        # state lives in fixed storage and is updated in place: a captured CUDA graph re-reads the same addresses
+        self.ego.copy_(torch.where(m[:, None], ego, self.ego))
+        self.oth.copy_(torch.where(m[:, None, None], oth, self.oth))
+        self.t.copy_(torch.where(m, torch.zeros_like(self.t), self.t))
+        self.crashed.copy_(self.crashed & ~m)
         return self.observe()
 
     def observe(self) -> torch.Tensor:
@@ -98,27 +122,23 @@ class BatchedIntersectionEnv:
         dist_ = torch.hypot(o[..., 0] - e[:, None, 0], o[..., 1] - e[:, None, 1])
         idx = torch.argsort(dist_, dim=1)
         o = torch.gather(o, 1, idx[..., None].expand(-1, -1, 4))
-        obs = torch.zeros(self.B, self.V, 8, device=self.device)
-        obs[:, :, 0] = 1.0
-        obs[:, 0, 1], obs[:, 0, 2] = e[:, 0], e[:, 1]
-        obs[:, 0, 3], obs[:, 0, 4] = e[:, 3] * torch.cos(e[:, 2]), e[:, 3] * torch.sin(e[:, 2])
-        obs[:, 0, 5], obs[:, 0, 6], obs[:, 0, 7] = e[:, 2], torch.sin(e[:, 2]), torch.cos(e[:, 2])
-        obs[:, 1:, 1], obs[:, 1:, 2] = o[..., 0], o[..., 1]
-        obs[:, 1:, 3], obs[:, 1:, 4] = o[..., 2] * torch.cos(o[..., 3]), o[..., 2] * torch.sin(o[..., 3])
-        obs[:, 1:, 5], obs[:, 1:, 6], obs[:, 1:, 7] = o[..., 3], torch.sin(o[..., 3]), torch.cos(o[..., 3])
-        return obs.contiguous()
+        x = torch.cat([e[:, None, 0], o[..., 0]], dim=1)
+        y = torch.cat([e[:, None, 1], o[..., 1]], dim=1)
+        spd = torch.cat([e[:, None, 3], o[..., 2]], dim=1)
+        hd = torch.cat([e[:, None, 2], o[..., 3]], dim=1)
+        sh, ch = torch.sin(hd), torch.cos(hd)
+        return torch.stack([torch.ones_like(x), x, y, spd * ch, spd * sh, hd, sh, ch], dim=-1).contiguous()
 
     def step(self, action: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, Dict[str, torch.Tensor]]:
         """action [B, 2] = (accel, steer) as the caller sends it.  Returns (obs, reward, done, info); finished
-        environments are reset in place (VecEnv semantics) and flagged in `done`."""
+        environments are reset in place (VecEnv semantics) and flagged in `done`; info["terminal_observation"]
+        holds the observation before that reset (meaningful in the rows where `done`)."""
         a = action.to(self.device).float()
         if self.action_scaling == "sb3_raw":               # agents/a2c_mpc.py:151-153 -> ContinuousAction clip + lmap (quirk Q8)
             acc = a[:, 0].clamp(-1, 1) * 5.0
             steer = a[:, 1].clamp(-1, 1) * (math.pi / 4)
-        elif self.action_scaling == "physical":
-            acc, steer = a[:, 0].clamp(-5, 5), a[:, 1].clamp(-math.pi / 4, math.pi / 4)
         else:
-            raise ValueError("action_scaling must be 'sb3_raw' or 'physical'")
+            acc, steer = a[:, 0].clamp(-5, 5), a[:, 1].clamp(-math.pi / 4, math.pi / 4)
         x, y, th, v = self.ego.unbind(1)
         beta = torch.atan(0.5 * torch.tan(steer))
         for _ in range(self.sub):                          # highway-env Vehicle.step at the simulation frequency
@@ -127,20 +147,17 @@ class BatchedIntersectionEnv:
             th = th + v * torch.sin(beta) / 2.5 * self.dt_sim
             v = (v + acc * self.dt_sim).clamp(-40.0, 40.0)
         th = torch.atan2(torch.sin(th), torch.cos(th))
-        self.ego = torch.stack([x, y, th, v], dim=1)
+        self.ego.copy_(torch.stack([x, y, th, v], dim=1))
         o = self.oth
         step_len = o[..., 2] * (self.sub * self.dt_sim)
         ox = o[..., 0] + step_len * torch.cos(o[..., 3])
         oy = o[..., 1] + step_len * torch.sin(o[..., 3])
-        gone = (ox.abs() > 90) | (oy.abs() > 90)
-        if bool(gone.any()):                               # _clear_vehicles + _spawn_vehicle stand-in
-            fresh = self._spawn_others(self.B)
-            far = fresh                                     # same lane geometry, placed at the map edge
-            far[..., 0] = torch.where(far[..., 3] == 0.0, -80.0, torch.where(far[..., 3] == math.pi, 80.0, far[..., 0]))
-            far[..., 1] = torch.where(far[..., 3] == -math.pi / 2, 80.0, torch.where(far[..., 3] == math.pi / 2, -80.0, far[..., 1]))
-            ox, oy = torch.where(gone, far[..., 0], ox), torch.where(gone, far[..., 1], oy)
-            o = torch.where(gone[..., None], far, o)
-        self.oth = torch.stack([ox, oy, o[..., 2], o[..., 3]], dim=-1)
+        gone = (ox.abs() > 90) | (oy.abs() > 90)           # _clear_vehicles + _spawn_vehicle stand-in: re-enter at the map edge
+        far = self._spawn_others()
+        fx = torch.where(far[..., 3] == 0.0, -80.0, torch.where(far[..., 3] == math.pi, 80.0, far[..., 0]))
+        fy = torch.where(far[..., 3] == -math.pi / 2, 80.0, torch.where(far[..., 3] == math.pi / 2, -80.0, far[..., 1]))
+        ox, oy = torch.where(gone, fx, ox), torch.where(gone, fy, oy)
+        self.oth.copy_(torch.stack([ox, oy, torch.where(gone, far[..., 2], o[..., 2]), torch.where(gone, far[..., 3], o[..., 3])], dim=-1))
         self.t += 1
         crashed = (torch.hypot(ox - x[:, None], oy - y[:, None]) < 2.5).any(dim=1)
         arrived = (x <= self.ref_xy[-2, 0]) & ((y - self.ref_xy[-1, 1]).abs() < 4.0)
@@ -149,12 +166,10 @@ class BatchedIntersectionEnv:
         reward = torch.where(arrived, torch.ones_like(reward), reward)
         truncated = self.t >= self.duration_steps
         done = crashed | arrived | truncated
-        info = {"crashed": crashed, "arrived": arrived, "truncated": truncated & ~(crashed | arrived), "speed": v.clone()}
-        if bool(done.any()):
-            info["terminal_observation"] = self.observe()   # rows of finished envs: the state before the in-place reset
-            obs = self.reset(done)
-        else:
-            obs = self.observe()
+        self.crashed.copy_(crashed)
+        info = {"crashed": crashed, "arrived": arrived, "truncated": truncated & ~(crashed | arrived), "speed": v.clone(),
+                "terminal_observation": self.observe()}
+        obs = self.reset(done)
         return obs, reward, done, info
 
 
@@ -192,15 +207,19 @@ class ActorCritic(nn.Module):
     def reset_noise(self, n_envs: int) -> None:
         if self.use_sde:
             std = self.log_std.detach().exp()
-            self._theta = torch.randn(n_envs, *std.shape, device=std.device) * std
+            theta = torch.randn(n_envs, *std.shape, device=std.device) * std
+            if self._theta is not None and self._theta.shape == theta.shape and self._theta.device == theta.device:
+                self._theta.copy_(theta)                      # same storage: a captured CUDA graph keeps reading it
+            else:
+                self._theta = theta
 
     def dist(self, obs):
         latent = self.mlp_extractor.policy_net(obs)
         mean = self.action_net(latent)
         if self.use_sde:
             var = (latent.detach() ** 2) @ (self.log_std.exp() ** 2)        # SB3: no gradient through the features
-            return torch.distributions.Normal(mean, torch.sqrt(var + 1e-6)), latent
-        return torch.distributions.Normal(mean, self.log_std.exp().expand_as(mean)), latent
+            return torch.distributions.Normal(mean, torch.sqrt(var + 1e-6), validate_args=False), latent
+        return torch.distributions.Normal(mean, self.log_std.exp().expand_as(mean), validate_args=False), latent   # validation would sync
 
     def forward(self, obs, deterministic: bool = False):
         d, latent = self.dist(obs)
@@ -211,7 +230,7 @@ class ActorCritic(nn.Module):
                 self.reset_noise(obs.shape[0])
             a = d.mean + torch.bmm(latent.detach().unsqueeze(1), self._theta).squeeze(1)
         else:
-            a = d.sample()
+            a = d.mean + d.stddev * torch.randn_like(d.mean)   # not d.sample(): torch.normal(tensor std) checks std >= 0 on the host
         return a, self.value(obs), d.log_prob(a).sum(-1)
 
     def evaluate_actions(self, obs, actions):
@@ -223,12 +242,16 @@ class _MPCRollout:
     """Rollout shared by the batched A2C-MPC and PPO-MPC: policy(obs) -> RL action -> MPC (reference speed in
     version "v0", the three objective weights in "v1") -> env.step(raw (a, delta)); the buffer stores the RL
     action (agents/a2c_mpc.py:111-180, agents/ppo_mpc.py:353-483).  Time-limit truncations bootstrap with the
-    value of the terminal observation as SB3 does (agents/ppo_mpc.py:451-461)."""
+    value of the terminal observation as SB3 does (agents/ppo_mpc.py:451-461).
+
+    graph=True (CUDA only): the whole transition -- policy forward, the MPC's two kernels, the env step, the
+    buffer writes -- is captured once in a CUDA graph and replayed n_steps times per rollout; graph=False runs
+    it eagerly with per-phase wall-clock shares in `stats`."""
 
     clip_rl_action = False      # PPO_MPC clips the sample to the Box before the MPC sees it (agents/ppo_mpc.py:399-408);
                                 # A2C_MPC hands the raw Gaussian sample over (SURVEY quirk Q6)
 
-    def _setup(self, env, mpc, version, action_dim, n_steps, gamma, gae_lambda, use_sde, seed):
+    def _setup(self, env, mpc, version, action_dim, n_steps, gamma, gae_lambda, use_sde, seed, graph=False):
         if version not in ("v0", "v1"):
             raise ValueError("version must be 'v0' (RL sets the reference speed) or 'v1' (RL sets the MPC weights)")
         self.env, self.mpc, self.version = env, mpc, version
@@ -239,10 +262,17 @@ class _MPCRollout:
         if dist.is_available() and dist.is_initialized():
             for p in self.policy.parameters():
                 dist.broadcast(p.data, 0)
-        self.obs = env.observe()
-        self.episode_start = torch.ones(env.B, dtype=torch.bool, device=env.device)
+        B, T, dev = env.B, n_steps, env.device
+        self.obs = env.observe().clone()                     # static storage: the captured transition updates it in place
+        self.episode_start = torch.ones(B, dtype=torch.bool, device=dev)
+        self._buf = {k: torch.zeros(T, B, device=dev) for k in ("rew", "val", "logp", "done")}
+        self._buf["act"] = torch.zeros(T, B, self.action_dim, device=dev)
+        self._obs_buf = torch.zeros(T, B, env.V * 8, device=dev)
+        self._row = torch.zeros(1, dtype=torch.int64, device=dev)      # row of the rollout buffer the next transition fills
+        self.graph = bool(graph) and dev.type == "cuda"
+        self._cuda_graph = None
         self.num_timesteps = 0
-        self.stats = {"mpc_s": 0.0, "env_s": 0.0, "policy_s": 0.0, "update_s": 0.0, "steps": 0}
+        self.stats = {"mpc_s": 0.0, "env_s": 0.0, "policy_s": 0.0, "update_s": 0.0, "rollout_s": 0.0, "steps": 0}
 
     def mpc_action(self, obs, rl_action, reset_mask=None):
         a = rl_action.clamp(-1.0, 1.0) if self.clip_rl_action else rl_action
@@ -250,42 +280,80 @@ class _MPCRollout:
             return self.mpc.predict_batch(obs, ref_speed=a[:, :1].contiguous(), reset_mask=reset_mask)
         return self.mpc.predict_batch(obs, weights=a[:, :3].contiguous(), reset_mask=reset_mask)
 
-    def collect_rollouts(self):
-        B, T, dev, A = self.env.B, self.n_steps, self.env.device, self.action_dim
-        buf = {k: torch.zeros(T, B, device=dev) for k in ("rew", "val", "logp", "done")}
-        buf["act"] = torch.zeros(T, B, A, device=dev)
-        obs_buf = torch.zeros(T, B, self.env.V * 8, device=dev)
-        cuda = dev.type == "cuda"
-        self.policy.reset_noise(B)                          # sde_sample_freq = -1: once per rollout
-        for t in range(T):
-            t0 = time.perf_counter()
-            with torch.no_grad():
-                flat = self.obs.reshape(B, -1)
-                a, v, lp = self.policy(flat)
-            if cuda:
-                torch.cuda.synchronize(dev)
-            t1 = time.perf_counter()
-            mpc_action = self.mpc_action(self.obs, a, self.episode_start)   # the latch of finished envs is cleared
-            if cuda:
-                torch.cuda.synchronize(dev)
-            t2 = time.perf_counter()
-            new_obs, rew, done, info = self.env.step(mpc_action)
-            trunc = info["truncated"]
-            if bool(trunc.any()):
-                with torch.no_grad():
-                    tv = self.policy.value(info["terminal_observation"].reshape(B, -1))
-                rew = rew + self.gamma * tv * trunc.float()
-            if cuda:
-                torch.cuda.synchronize(dev)
-            t3 = time.perf_counter()
-            obs_buf[t], buf["act"][t], buf["rew"][t], buf["val"][t], buf["logp"][t] = flat, a, rew, v, lp
-            buf["done"][t] = done.float()
-            self.obs, self.episode_start = new_obs, done
+    @torch.no_grad()
+    def _transition(self, timed: bool = False):
+        """One policy -> MPC -> env transition written to row `_row` of the rollout buffers.  No host
+        synchronisation unless `timed` (per-phase wall clock for the eager profile)."""
+        B, dev = self.env.B, self.env.device
+        sync = (lambda: torch.cuda.synchronize(dev)) if (timed and dev.type == "cuda") else (lambda: None)
+        t0 = time.perf_counter()
+        flat = self.obs.reshape(B, -1)
+        a, v, lp = self.policy(flat)
+        sync()
+        t1 = time.perf_counter()
+        mpc_action = self.mpc_action(self.obs, a, self.episode_start)   # the latch of finished envs is cleared
+        sync()
+        t2 = time.perf_counter()
+        new_obs, rew, done, info = self.env.step(mpc_action)
+        tv = self.policy.value(info["terminal_observation"].reshape(B, -1))
+        rew = rew + self.gamma * tv * info["truncated"].float()         # time-limit bootstrap (agents/ppo_mpc.py:451-461)
+        sync()
+        t3 = time.perf_counter()
+        r = self._row
+        self._obs_buf.index_copy_(0, r, flat.unsqueeze(0))
+        self._buf["act"].index_copy_(0, r, a.unsqueeze(0))
+        self._buf["rew"].index_copy_(0, r, rew.unsqueeze(0))
+        self._buf["val"].index_copy_(0, r, v.unsqueeze(0))
+        self._buf["logp"].index_copy_(0, r, lp.unsqueeze(0))
+        self._buf["done"].index_copy_(0, r, done.float().unsqueeze(0))
+        self.obs.copy_(new_obs)
+        self.episode_start.copy_(done)
+        self._row += 1
+        if timed:
             self.stats["policy_s"] += t1 - t0
             self.stats["mpc_s"] += t2 - t1
             self.stats["env_s"] += t3 - t2
-            self.stats["steps"] += B
+
+    def _capture(self):
+        """Captures `_transition` into a CUDA graph (a few hundred small launches + the two MPC kernels become
+        one replay): warm up on a side stream, then capture.  The MPC launches are recorded through the C ABI
+        on torch's capturing stream; all operands live in static storage."""
+        dev = self.env.device
+        self.policy.reset_noise(self.env.B)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self._row.zero_()
+                self._transition()
+            self._row.zero_()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._transition()
+        self._cuda_graph = g
+
+    def collect_rollouts(self):
+        B, T, dev = self.env.B, self.n_steps, self.env.device
+        if self.graph and self._cuda_graph is None:
+            self._capture()
+        self.policy.reset_noise(B)                          # sde_sample_freq = -1: once per rollout
+        self._row.zero_()
+        if dev.type == "cuda":
+            torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(T):
+            if self._cuda_graph is not None:
+                self._cuda_graph.replay()
+            else:
+                self._transition(timed=True)
+        if dev.type == "cuda":
+            torch.cuda.synchronize(dev)
+        self.stats["rollout_s"] += time.perf_counter() - t0
+        self.stats["steps"] += B * T
         self.num_timesteps += B * T
+        buf, obs_buf = self._buf, self._obs_buf
         with torch.no_grad():
             last_v = self.policy.value(self.obs.reshape(B, -1))
         adv = torch.zeros(T, B, device=dev)
@@ -323,8 +391,8 @@ class A2CMPC(_MPCRollout):
     def __init__(self, env: BatchedIntersectionEnv, mpc, n_steps: int = 64, lr: float = 7e-4, gamma: float = 0.99,
                  gae_lambda: float = 1.0, ent_coef: float = 0.0, vf_coef: float = 0.5, max_grad_norm: float = 0.5,
                  rms_prop_eps: float = 1e-5, seed: int = 0, version: str = "v0", action_dim: Optional[int] = None,
-                 use_sde: bool = False):
-        self._setup(env, mpc, version, action_dim, n_steps, gamma, gae_lambda, use_sde, seed)
+                 use_sde: bool = False, graph: bool = False):
+        self._setup(env, mpc, version, action_dim, n_steps, gamma, gae_lambda, use_sde, seed, graph)
         self.ent_coef, self.vf_coef, self.max_grad_norm = ent_coef, vf_coef, max_grad_norm
         self.opt = torch.optim.RMSprop(self.policy.parameters(), lr=lr, alpha=0.99, eps=rms_prop_eps)
 
@@ -358,8 +426,9 @@ class PPOMPC(_MPCRollout):
                  n_epochs: int = 10, lr: float = 3e-4, gamma: float = 0.99, gae_lambda: float = 0.95,
                  clip_range: float = 0.2, clip_range_vf: Optional[float] = None, normalize_advantage: bool = True,
                  ent_coef: float = 0.0, vf_coef: float = 0.5, max_grad_norm: float = 0.5, target_kl: Optional[float] = None,
-                 use_sde: bool = True, seed: int = 0, version: str = "v0", action_dim: Optional[int] = None):
-        self._setup(env, mpc, version, action_dim, n_steps, gamma, gae_lambda, use_sde, seed)
+                 use_sde: bool = True, seed: int = 0, version: str = "v0", action_dim: Optional[int] = None,
+                 graph: bool = False):
+        self._setup(env, mpc, version, action_dim, n_steps, gamma, gae_lambda, use_sde, seed, graph)
         self.batch_size = batch_size if batch_size is not None else 256 * env.B
         self.n_epochs, self.clip_range, self.clip_range_vf = n_epochs, clip_range, clip_range_vf
         self.normalize_advantage, self.target_kl = normalize_advantage, target_kl

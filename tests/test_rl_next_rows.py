@@ -171,3 +171,27 @@ def test_ppo_mpc_and_evaluation_gpu():
     assert res["pure_mpc"]["episodes"] == B and res["mpcrl"]["episodes"] == B
     # the collision-aware MPC on the raw action path drives: it moves and most episodes end without a crash
     assert res["pure_mpc"]["avg_speed"] > 1.0 and res["pure_mpc"]["collision_rate"] < 0.6
+
+
+@pytest.mark.gpu
+def test_graph_captured_rollout_gpu():
+    """The policy -> MPC -> env transition replayed from a CUDA graph fills the same buffers as the eager loop."""
+    import mpc_rl_for_avs_b200 as pkg
+    from mpc_rl_for_avs_b200.rl import A2CMPC, PPOMPC, BatchedIntersectionEnv
+    B, T = 512, 12
+    cfg = {"horizon": 16, "weight_speed": 1, "weight_control": 1, "weight_input_diff": 1}
+    for Algo in (A2CMPC, PPOMPC):
+        mpc = pkg.BatchedPureMPC(cfg, vehicles_count=10, max_batch=B, collision_check=True)
+        algo = Algo(BatchedIntersectionEnv(B, 9, device="cuda", seed=9, duration_steps=20), mpc, n_steps=T, graph=True)
+        for _ in range(3):
+            log = algo.train_step()
+        assert algo._cuda_graph is not None and all(np.isfinite(v) for v in log.values())
+        assert int(algo._row) == T and algo.num_timesteps == 3 * B * T
+        obs_buf, buf = algo._obs_buf, algo._buf
+        assert (obs_buf[:, :, 0] == 1).all() and torch.isfinite(obs_buf).all()         # every row written (presence flag of the ego)
+        assert (obs_buf[1:] != obs_buf[:-1]).any(dim=-1).all()                          # the scene moves every step
+        assert 0.0 < float(buf["done"].mean()) < 0.5                                    # 20-step episodes end inside the rollout
+        assert torch.isfinite(buf["rew"]).all() and float(buf["act"].abs().max()) > 0
+        # the MPC really ran inside the graph: fresh iteration counts and bounded actions
+        assert int(mpc.iters[:B].max()) > 0 and float(mpc.actions[:B, 0].abs().max()) <= 5.0 + 1e-5
+        assert int(mpc.collision_memory[:B].max()) <= 10
