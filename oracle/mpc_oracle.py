@@ -5,16 +5,29 @@ reference's per-step MPC (SaeedRahmani/MPC-RL_for_AVs).  It is the *checker* for
 CUDA path.  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU legs may
 import it; the product package must never route through it.
 
-PARITY UNPINNED.  The reference's arithmetic for this path lives in third-party wheels
-that are absent from /root/reference and not installable here: ``casadi==3.6.6``
-(SX graph + IPOPT/MUMPS; reference requirements.txt:4) and ``shapely==2.0.6`` (GEOS;
-requirements.txt:7).  The reference holds no golden vectors, known-answer tests or
-fixtures for the path (its test_*.py are GUI demos).  What can be pinned from the
-reference source alone -- the 85x4 reference path table -- is pinned in
-tests/test_oracle.py.  Everything else below follows the reference's *published
-formulation* (call sites cited per function) and solves the same NLP with an
-independent method (scipy SLSQP on the single-shooting form; the literal
-multiple-shooting form of pure_mpc.py:230-300 is provided for cross-checks), with a
+PARITY: PINNED TO THE REFERENCE'S OWN CODE EXCEPT FOR TWO THIRD-PARTY PRIMITIVES.
+The reference holds no golden vectors, known-answer tests or fixtures for this path (its test_*.py
+are GUI demos), and its two native dependencies are absent and not installable here:
+``casadi==3.6.6`` (SX graph + IPOPT/MUMPS; requirements.txt:4) and ``shapely==2.0.6`` (GEOS;
+requirements.txt:7).  What was done instead (tests/golden/make_reference_golden.py ->
+tests/golden/golden_reference.npz, checked by tests/test_reference_pin.py):
+the UNMODIFIED agents/pure_mpc.py and agents/archive/pure_mpc.py are imported from /root/reference
+and executed with numeric stand-ins for casadi (numbers instead of symbols: every cost / constraint
+expression is evaluated by the reference's own lines at an injected trajectory) and shapely (textbook
+segment intersection).  Against those outputs this module is
+  * exact on every discrete output: nearest path index, per-vehicle collision flags, conflict indices,
+    is_collide, the 10-step latch over 16-step sequences (192 scenes + 24 x 16 sequence steps, 0 mismatches);
+  * within 4e-8 relative on the shipped objective and its components, 2e-6 on parsed state and
+    regenerated speeds, 1.3e-4 relative on the archive's obstacle-distance term -- all of it one
+    quirk (Q11): under the reference's pinned numpy 2.x, np.float32 scalars stay float32 against
+    Python floats (NEP 50), so the reference carries the ego speed, a wrapped heading and the other
+    vehicles' predicted positions in float32; this module uses float64 on the exact float32 inputs
+    (what the same reference computes under numpy 1.x promotion);
+  * identical bounds, cold start and dynamics constraints (the rollout below zeroes the reference's g).
+STILL UNPINNED: GEOS' intersection primitive (incl. the order of MultiPoint members: assumed
+lexicographic) and which local optimum IPOPT returns from the cold start.  For the latter the NLP is
+solved here by an independent method (scipy SLSQP on the single-shooting form; the literal
+multiple-shooting form of pure_mpc.py:230-300 is provided for cross-checks) with a
 solver-independent KKT certificate (`kkt_residual`).
 
 State order [x, y, theta, v], control order [a, delta]  (agents/pure_mpc.py:88-89).

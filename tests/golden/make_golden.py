@@ -3,7 +3,8 @@
     OMP_NUM_THREADS=1 python tests/golden/make_golden.py
 
 The reference itself cannot be imported here (casadi / shapely / highway-env are not installable,
-SURVEY 8-c), so these vectors pin the ORACLE, not CasADi/IPOPT ("parity unpinned").  Files:
+SURVEY 8-c), so these vectors hold the ORACLE's solutions, not CasADi/IPOPT's; the oracle itself is pinned to
+the reference's own code by make_reference_golden.py / golden_reference.npz.  Files:
   golden_track.npz   256 scenarios, M=0, tracking objective (BASELINE config 2 type)
   golden_coll.npz    256 scenarios, M=8, collision check + regeneration + distance cost 10 (config 3 type)
 Each holds the observations (float32), the parsed problem descriptors, collision outputs and the

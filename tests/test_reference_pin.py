@@ -1,0 +1,139 @@
+"""The oracle AND the CUDA path against outputs of the REFERENCE'S OWN CODE (tests/golden/golden_reference.npz,
+made by tests/golden/make_reference_golden.py: the unmodified agents/pure_mpc.py and agents/archive/pure_mpc.py
+run with numeric stand-ins for casadi / shapely).  What this pins: observation parsing, nearest path index,
+collision flags and conflict indices, the 10-step latch, reference-speed regeneration, the NLP's objective,
+components, dynamics constraints, bounds and cold start.  What it cannot pin: GEOS' intersection primitive
+(stand-in) and IPOPT's choice of local optimum.
+
+Tolerances.  Discrete outputs: exact.  Continuous: the reference, under its pinned numpy 2.x, carries the ego
+speed, a wrapped heading and the other vehicles' predicted positions in FLOAT32 (np.float32 scalars stay
+float32 against Python floats, NEP 50); the oracle and the kernels use the float64 / exact-input values.
+Measured effect (this fixture): ego speed / heading <= 1e-6, regenerated speeds <= 1e-6, shipped objective
+<= 4e-8 relative, archive distance component <= 1.3e-4 relative (close obstacles, 1/d^2).  The tests allow
+a small multiple of those.
+"""
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from helpers import orc
+
+G = helpers.load_golden("golden_reference")
+S, V = G["obs"].shape[0], G["obs"].shape[1]
+M, N = V - 1, 20
+CFG = {"horizon": N, "weight_speed": 1.0, "weight_control": 1.0, "weight_input_diff": 1.0}
+
+
+def _cidx(agent_conflict, n):
+    out = -np.ones(M, np.int32)
+    if len(agent_conflict) == n:
+        out[:n] = [-1 if c is None else c for c in agent_conflict]
+    return out
+
+
+def test_fixture_is_the_reference_problem():
+    """Bounds, cold start and dynamics of agents/pure_mpc.py:230-300 as the reference itself evaluated them."""
+    lb, ub = G["lbx"], G["ubx"]
+    assert lb.shape == (6 * N + 4,)
+    assert np.array_equal(lb[:4], [-500, -500, -np.pi, 0]) and np.array_equal(ub[:4], [500, 500, np.pi, 30])
+    assert np.array_equal(lb[-2:], [-5, -np.pi / 3]) and np.array_equal(ub[-2:], [5, np.pi / 3])
+    assert (orc.A_MAX, orc.DELTA_MAX, orc.V_MIN, orc.V_MAX, orc.TH_MAX) == (5.0, np.pi / 3, 0.0, 30.0, np.pi)
+    # cold start: the parsed state tiled over the horizon, zero controls
+    x0 = G["ss_x0"]
+    assert np.all(x0[:, 4 * (N + 1):] == 0)
+    assert np.array_equal(x0[:, :4 * (N + 1)].reshape(S, N + 1, 4), np.repeat(G["ss_ego_state"][:, None, :], N + 1, axis=1))
+    # the oracle's rollout satisfies the reference's dynamics constraints: the only residual is the float32
+    # speed / wrapped heading of the initial condition
+    assert np.all(G["ss_g_max"] <= 1e-6) and np.all(np.abs(G["ss_g0"][:, :2]) == 0)
+    assert float(np.mean(G["ss_is_collide"])) > 0.2 and float(np.mean(G["seq_is_collide"])) > 0.2
+
+
+def test_oracle_single_step_against_reference():
+    for i in range(S):
+        ag = orc.OraclePureMPCAgent(horizon=N, vehicles_count=V, collision_check=True)
+        rs = np.array([[G["ref_speed"][i]]]) if G["has_ref_speed"][i] else None
+        parsed = orc.parse_obs(G["obs"][i], V)
+        assert np.abs(parsed.ego - G["ss_ego_state"][i]).max() <= 2e-6
+        ag.check_collision(parsed)
+        prob = ag.build_problem(parsed, ref_speed=rs)
+        assert prob.ego_index == G["ss_ego_index"][i]
+        assert bool(prob.is_collide) == bool(G["ss_is_collide"][i]) and ag.collision_memory == G["ss_memory"][i]
+        n = parsed.others.shape[0]
+        if len(ag.conflict_index) == n:
+            assert np.array_equal(_cidx(ag.conflict_index, n), G["ss_cidx"][i]), i
+        j = np.minimum(prob.ego_index + np.arange(N), orc.N_REF - 1)
+        assert np.abs(prob.ref_v - G["ss_ref_v"][i][j]).max() <= 2e-6
+        U = G["ss_U"][i]
+        J = orc.objective(U, prob)
+        assert abs(J - G["ss_f"][i]) <= 1e-6 * max(1.0, abs(G["ss_f"][i])), i
+        comp = np.asarray(orc.cost_components(orc.rollout(prob.s0, U), U, prob))
+        ref = G["ss_components"][i]
+        assert np.all(np.abs(comp[:4] - ref[:4]) <= 1e-6 * np.maximum(1.0, np.abs(ref[:4]))), i   # state, control, final_state, input_diff
+        assert ref[4] == 0 and ref[5] == 0                     # shipped file: distance / collision terms disabled (quirk Q2)
+        # the archive file's distance term (BASELINE config 3), evaluated by the archive file itself
+        assert abs(comp[4] - G["ss_distance_component"][i]) <= 5e-4 * max(1.0, abs(G["ss_distance_component"][i])), i
+
+
+def test_oracle_latch_sequences_against_reference():
+    Q, T = G["seq_obs"].shape[:2]
+    for q in range(Q):
+        ag = orc.OraclePureMPCAgent(horizon=N, vehicles_count=V, collision_check=True)
+        for t in range(T):
+            parsed = orc.parse_obs(G["seq_obs"][q, t], V)
+            ag.check_collision(parsed)
+            prob = ag.build_problem(parsed)
+            assert bool(ag.is_collide) == bool(G["seq_is_collide"][q, t]) and ag.collision_memory == G["seq_memory"][q, t], (q, t)
+            assert prob.ego_index == G["seq_ego_index"][q, t]
+            assert np.array_equal(_cidx(ag.conflict_index, parsed.others.shape[0]), G["seq_cidx"][q, t]), (q, t)
+            j = np.minimum(prob.ego_index + np.arange(N), orc.N_REF - 1)
+            assert np.abs(prob.ref_v - G["seq_ref_v"][q, t][j]).max() <= 2e-6
+
+
+# ------------------------------------------------------------------------------------------------- CUDA path
+def _profile(ws):
+    k = np.arange(N)[None, :]
+    return np.where(k < ws["vr_n"][:, None], ws["vr_a"][:, None] + k * ws["vr_slope"][:, None], ws["vr_b"][:, None])
+
+
+@pytest.mark.gpu
+def test_cuda_prepare_and_cost_against_reference():
+    import mpc_rl_for_avs_b200 as pkg
+    agent = pkg.BatchedPureMPC(CFG, vehicles_count=V, max_batch=S, collision_check=True, weight_distance=0.0)
+    rs = np.where(G["has_ref_speed"], G["ref_speed"], np.nan).astype(np.float32)
+    ws_t = agent.prepare_batch(torch.from_numpy(G["obs"]).cuda(), ref_speed=torch.from_numpy(rs).cuda())
+    ws = {k: v.cpu().numpy() for k, v in ws_t.items()}
+    assert np.array_equal(ws["ego_index"], G["ss_ego_index"])
+    assert np.array_equal(ws["is_collide"].astype(bool), G["ss_is_collide"].astype(bool))
+    assert np.array_equal(agent.collision_memory[:S].cpu().numpy(), G["ss_memory"])
+    n_obs = ws["n_obs"]
+    flags, cidx = agent.agent_collide[:S].cpu().numpy(), agent.conflict_index[:S].cpu().numpy()
+    for i in range(S):
+        assert np.array_equal(flags[i, :n_obs[i]].astype(bool), G["ss_flags"][i, :n_obs[i]].astype(bool)), i
+        assert np.array_equal(cidx[i, :n_obs[i]], G["ss_cidx"][i, :n_obs[i]]), i
+    assert np.abs(ws["s0"].T - G["ss_ego_state"]).max() <= 4e-6
+    j = np.minimum(G["ss_ego_index"][:, None] + np.arange(N)[None, :], 84)
+    ref_v = np.take_along_axis(G["ss_ref_v"], j, axis=1)
+    assert np.abs(_profile(ws) - ref_v).max() <= 1e-5
+    # objective and components of the reference's NLP at the injected controls: FP32 kernel vs the reference's FP64 numbers
+    X, c6, tot = agent.rollout_cost(ws_t, torch.from_numpy(G["ss_U"].astype(np.float32)).cuda())
+    X, c6, tot = X.cpu().numpy().astype(np.float64), c6.cpu().numpy().astype(np.float64), tot.cpu().numpy().astype(np.float64)
+    assert np.all(np.abs(X - G["ss_X"]) <= 1e-5 * np.maximum(1.0, np.abs(G["ss_X"])) + 5e-6)
+    assert np.all(np.abs(tot - G["ss_f"]) <= 1e-5 * np.maximum(1.0, np.abs(G["ss_f"])))
+    ref = G["ss_components"]
+    assert np.all(np.abs(c6[:, :4] - ref[:, :4]) <= 1e-5 * np.maximum(1.0, np.abs(ref[:, :4])))
+
+
+@pytest.mark.gpu
+def test_cuda_latch_sequences_against_reference():
+    import mpc_rl_for_avs_b200 as pkg
+    Q, T = G["seq_obs"].shape[:2]
+    agent = pkg.BatchedPureMPC(CFG, vehicles_count=V, max_batch=Q, collision_check=True)
+    for t in range(T):
+        ws = agent.prepare_batch(torch.from_numpy(np.ascontiguousarray(G["seq_obs"][:, t])).cuda())
+        ws = {k: v.cpu().numpy() for k, v in ws.items()}
+        assert np.array_equal(ws["is_collide"].astype(bool), G["seq_is_collide"][:, t].astype(bool)), t
+        assert np.array_equal(agent.collision_memory[:Q].cpu().numpy(), G["seq_memory"][:, t]), t
+        assert np.array_equal(ws["ego_index"], G["seq_ego_index"][:, t]), t
+        j = np.minimum(G["seq_ego_index"][:, t][:, None] + np.arange(N)[None, :], 84)
+        assert np.abs(_profile(ws) - np.take_along_axis(G["seq_ref_v"][:, t], j, axis=1)).max() <= 1e-5, t
