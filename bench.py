@@ -163,14 +163,16 @@ def main() -> None:
         batches.append((obs.contiguous(), rsn))
     dev_batches = [(o.to(dev), r.to(dev)) for o, r in batches]
     host_batches = [(o.pin_memory(), r.pin_memory()) for o, r in batches]
-    gathered = torch.empty(total, 2, dtype=torch.float32, device=dev) if world > 1 else None
+    gatherer = pkg.sharding.ActionGather(total, dev) if world > 1 else None
+    if gatherer is not None:
+        agent.bind_actions(gatherer.local)       # k_solve writes this rank's actions into its slice of the gathered buffer
 
     def step(i):
         o, r = dev_batches[i % n_unique]
         agent.reset()
         a = agent.predict_batch(o, ref_speed=r)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, a.contiguous())
+        if gatherer is not None:
+            gatherer.gather()                    # in-place NCCL all-gather: every rank ends up with all actions
         return a
 
     def barrier():
@@ -216,8 +218,9 @@ def main() -> None:
     def e2e_step(i):
         o, r = host_np[i % n_unique]
         acts, stat, iscol, up, down = agent.predict_host(o, r, reset_mask=reset_all)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, torch.from_numpy(acts).to(dev))
+        if gatherer is not None:
+            gatherer.local.copy_(torch.from_numpy(acts), non_blocking=True)
+            gatherer.gather()
         return up, down
 
     for i in range(3):

@@ -127,6 +127,18 @@ class BatchedPureMPC:
             self.memo_conflict[:n][m] = -1
             self.latch_is_collide[:n][m] = 0
 
+    def bind_actions(self, actions: Optional[torch.Tensor]) -> None:
+        """Redirects the solver's action output to a caller-owned [>= max_batch, 2] float32 buffer on this
+        device (e.g. this rank's slice of `sharding.ActionGather.buffer`, so the collective needs no copy).
+        None restores the agent's own buffer."""
+        if actions is None:
+            self.actions = torch.zeros(self.max_batch, 2, dtype=torch.float32, device=self.device)
+            return
+        if (actions.device != self.device or actions.dtype != torch.float32 or not actions.is_contiguous()
+                or actions.dim() != 2 or actions.shape[1] != 2):
+            raise ValueError("actions must be a contiguous float32 [n, 2] tensor on this agent's CUDA device")
+        self.actions = actions
+
     # ------------------------------------------------------------------ helpers
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
@@ -136,8 +148,8 @@ class BatchedPureMPC:
             raise TypeError(f"Expect observation type torch.Tensor, but got {type(obs)}.")
         if obs.dim() != 3 or tuple(obs.shape[1:]) != (self.vehicles_count, 8):
             raise ValueError(f"Expect observation's shape of (B, {self.vehicles_count}, 8), but got {tuple(obs.shape)}")
-        if obs.shape[0] > self.max_batch:
-            raise ValueError(f"batch {obs.shape[0]} exceeds max_batch {self.max_batch}")
+        if obs.shape[0] > self.max_batch or obs.shape[0] > self.actions.shape[0]:
+            raise ValueError(f"batch {obs.shape[0]} exceeds max_batch {self.max_batch} / the bound action buffer")
         if obs.device != self.device or obs.dtype != torch.float32 or not obs.is_contiguous():
             raise ValueError("obs must be a contiguous float32 tensor on this agent's CUDA device")
         return int(obs.shape[0])

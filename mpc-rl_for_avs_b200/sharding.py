@@ -45,3 +45,35 @@ def all_gather_actions(local_actions: torch.Tensor, total: int) -> torch.Tensor:
 def _gather_list(out: torch.Tensor, pad: torch.Tensor, world: int, nmax: int) -> None:
     chunks = [out[r * nmax:(r + 1) * nmax] for r in range(world)]
     dist.all_gather(chunks, pad)
+
+
+class ActionGather:
+    """In-place all-gather of the actions: one persistent [world * n_max, 2] buffer per rank; the
+    solve kernel writes this rank's actions straight into its slice (`BatchedPureMPC.bind_actions(g.local)`),
+    and `gather()` runs the collective with the slice as send buffer and the whole buffer as receive buffer
+    (NCCL's in-place form: no staging copy, no per-step allocation).  `full` is the [total, 2] result in env
+    order; with uneven shards (total % world != 0) the padding rows are skipped by a gather of row indices."""
+
+    def __init__(self, total: int, device, dtype=torch.float32):
+        init = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size() if init else 1
+        self.rank = dist.get_rank() if init else 0
+        self.total = int(total)
+        sizes = [shard_range(total, r, self.world) for r in range(self.world)]
+        self.lo, self.hi = sizes[self.rank]
+        self.n_max = max(hi - lo for lo, hi in sizes)
+        self.buffer = torch.zeros(self.world * self.n_max, 2, dtype=dtype, device=device)
+        self.local = self.buffer[self.rank * self.n_max: self.rank * self.n_max + (self.hi - self.lo)]
+        self._send = self.buffer[self.rank * self.n_max: (self.rank + 1) * self.n_max]
+        self._even = all(hi - lo == self.n_max for lo, hi in sizes)
+        if not self._even:
+            rows = [r * self.n_max + k for r, (lo, hi) in enumerate(sizes) for k in range(hi - lo)]
+            self._rows = torch.tensor(rows, dtype=torch.int64, device=device)
+
+    def gather(self) -> torch.Tensor:
+        if self.world > 1:
+            if self.buffer.is_cuda:
+                dist.all_gather_into_tensor(self.buffer, self._send)
+            else:                                            # gloo (CPU tests): list form on views of the same buffer
+                dist.all_gather([self.buffer[r * self.n_max:(r + 1) * self.n_max] for r in range(self.world)], self._send.clone())
+        return self.buffer[: self.total] if self._even else self.buffer.index_select(0, self._rows)

@@ -336,6 +336,28 @@ def test_result_independent_of_batch_size():
     assert len(seen) >= 4          # both kernels and several block sizes were exercised
 
 
+def test_actions_written_into_a_bound_buffer():
+    """`bind_actions`: the solve kernel writes into a caller-owned buffer (the rank's slice of the all-gather buffer)."""
+    pkg = _pkg()
+    B, M = 2048, 8
+    obs, rs, has = pkg.make_scenarios(B, M, seed=5)
+    agent = pkg.BatchedPureMPC(CFG, vehicles_count=M + 1, max_batch=B, collision_check=True, weight_distance=10.0)
+    a0 = agent.predict_batch(obs.cuda()).clone()
+    g = pkg.sharding.ActionGather(B, "cuda")               # single process: world 1, the slice is the whole buffer
+    agent.bind_actions(g.local)
+    agent.reset()
+    a1 = agent.predict_batch(obs.cuda())
+    assert a1.data_ptr() == g.buffer.data_ptr() and torch.equal(g.gather(), a0)
+    with pytest.raises(ValueError):
+        agent.bind_actions(torch.zeros(4, 2))              # wrong device
+    agent.bind_actions(torch.zeros(16, 2, device="cuda"))
+    with pytest.raises(ValueError):
+        agent.predict_batch(obs.cuda())                    # bound buffer too small for this batch
+    agent.bind_actions(None)
+    agent.reset()
+    assert torch.equal(agent.predict_batch(obs.cuda()), a0)
+
+
 def test_edge_cases():
     pkg = _pkg()
     M = 8

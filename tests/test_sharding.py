@@ -31,6 +31,13 @@ def _worker(rank, world, port, total, q):
     idx = torch.arange(lo, hi, dtype=torch.float32)
     local = torch.stack([idx, -2 * idx], dim=1)
     full = all_gather_actions(local, total)
+    # in-place form: the producer writes into its slice of the persistent gathered buffer
+    from mpc_rl_for_avs_b200.sharding import ActionGather
+    g = ActionGather(total, "cpu")
+    assert g.local.shape[0] == hi - lo and g.local.data_ptr() == g.buffer[rank * g.n_max].data_ptr()
+    for rep in range(2):                                  # the buffer is reused step after step
+        g.local.copy_(local + rep)
+        assert torch.equal(g.gather(), full + rep)
     q.put((rank, full.numpy()))
     dist.barrier()
     dist.destroy_process_group()
