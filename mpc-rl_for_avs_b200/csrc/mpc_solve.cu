@@ -174,16 +174,20 @@ k_solve(const SolverConfig cfg, const MpcProblemBatch batch, const MpcSolveOut o
 //     cells.  Under SIMT those lanes were waiting anyway.
 //   * shared memory per problem is 156 words -> 352 problems resident per SM (192 with gains in shared memory).
 constexpr int kTmemColsPerStage = 8;
+// Tail compaction (k_solve_tmem, blocks of <= 256 threads): scratch for moving up to kCompactMax problems'
+// register state between lanes, plus one counter per warp.
+constexpr int kCompactMax = 128, kCompactWords = 28, kCompactTpbMax = 256;
+static constexpr int compact_floats(int tpb) { return (tpb > 128 && tpb <= kCompactTpbMax) ? kCompactMax * kCompactWords + 16 : 0; }
 size_t solve_smem_bytes_tmem(int N, int M, int tpb) {
-  return (size_t)(kTabFloats + 4 + slots_per_problem_tmem(N, M) * tpb) * sizeof(float);
+  return (size_t)(kTabFloats + 4 + slots_per_problem_tmem(N, M) * tpb + compact_floats(tpb)) * sizeof(float);
 }
 bool tmem_layout_fits(int N, int tpb) {
   const int warps = tpb / 32, per_quarter = (warps + 3) / 4;
   return kTmemColsPerStage * N * per_quarter <= 512;
 }
 
-#ifndef MPC_BLOCK_SYNC
-#define MPC_BLOCK_SYNC 0
+#ifndef MPC_COMPACT
+#define MPC_COMPACT 1
 #endif
 
 template <int TPB>
@@ -203,9 +207,16 @@ k_solve_tmem(const SolverConfig cfg, const MpcProblemBatch batch, const MpcSolve
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem_base = *s_tmem;
   using SL = SlotsTmem<TPB>;
-  const SL sl{smem + kTabFloats + 4 + threadIdx.x,
-              tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(kTmemColsPerStage * cfg.N * (warp >> 2)), cfg.N, cfg.M};
+  float* const slot0 = smem + kTabFloats + 4;
+  SL sl{slot0 + threadIdx.x,
+        tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(kTmemColsPerStage * cfg.N * (warp >> 2)), cfg.N, cfg.M};
   const unsigned full = 0xffffffffu;
+  constexpr bool kCompact = (MPC_COMPACT != 0) && TPB > 128 && TPB <= kCompactTpbMax;   // <= 4 warps already have a scheduler each
+  uint32_t* const scratch = reinterpret_cast<uint32_t*>(slot0 + slots_per_problem_tmem(cfg.N, cfg.M) * TPB);
+  int* const s_wcnt = reinterpret_cast<int*>(scratch + kCompactMax * kCompactWords);
+  int live_warps = TPB / 32;                                // warps that may still hold problems (block-uniform)
+  bool drained = false;                                     // some lane of the block found the queue empty (block-uniform)
+  bool saw_empty = false;                                   // this lane did
 
   ProblemScalars<float> p;
   p.x0 = 0.0; p.y0 = 0.0; p.ego_index = 0; p.n_obs = 0; p.is_collide = 0;
@@ -231,14 +242,65 @@ k_solve_tmem(const SolverConfig cfg, const MpcProblemBatch batch, const MpcSolve
           }
         }
         fresh = true;
+      } else {
+        saw_empty = true;
       }
     }
     __syncwarp();
-#if MPC_BLOCK_SYNC >= 1
-    if (!__syncthreads_or(active)) break;
-#else
-    if (!__any_sync(full, active)) break;
-#endif
+    if (kCompact) {
+      // ---- one block barrier per trip: count the running problems; once the queue is drained and they fit
+      // into half of the warps that still hold any, move them to the lowest lanes.  The launch ends with a
+      // tail of a few long problems per SM, and one trip of a warp takes 71 us with two warps per scheduler
+      // but 56 us with one: packing the survivors into <= 4 (then 2, then 1) warps shortens every trip of
+      // the tail.  A problem's state is 25 registers + its shared-memory column (re-pointed, not copied);
+      // the gains in TMEM are rebuilt by the next backward sweep, so nothing else moves.
+      const int n_active = __syncthreads_count(active);
+      if (n_active == 0) break;
+      if (!drained) drained = __syncthreads_or(saw_empty) != 0;     // every decision below is taken on barrier results only
+      if (drained && live_warps > 1 && n_active <= 16 * live_warps && n_active <= kCompactMax) {
+        const unsigned bal = __ballot_sync(full, active);
+        const int lane = threadIdx.x & 31;
+        if (lane == 0) s_wcnt[warp] = __popc(bal);
+        __syncthreads();
+        if (active) {
+          int r = __popc(bal & ((1u << lane) - 1u));
+          for (int w = 0; w < warp; ++w) r += s_wcnt[w];
+          uint32_t* q = scratch + r * kCompactWords;
+          q[0] = (uint32_t)__double2loint(p.x0); q[1] = (uint32_t)__double2hiint(p.x0);
+          q[2] = (uint32_t)__double2loint(p.y0); q[3] = (uint32_t)__double2hiint(p.y0);
+          q[4] = (uint32_t)p.ego_index; q[5] = (uint32_t)p.n_obs; q[6] = (uint32_t)p.is_collide;
+          q[7] = __float_as_uint(p.w_speed); q[8] = __float_as_uint(p.w_control); q[9] = __float_as_uint(p.w_diff);
+          q[10] = __float_as_uint(p.vr_a); q[11] = __float_as_uint(p.vr_slope); q[12] = __float_as_uint(p.vr_b);
+          q[13] = (uint32_t)p.vr_n;
+          q[14] = __float_as_uint(s.J); q[15] = __float_as_uint(s.mu);    // s.hs is the constant 1 in every kernel: kept out of memory so it still folds
+          q[17] = __float_as_uint(s.J_mark); q[18] = (uint32_t)s.iter; q[19] = (uint32_t)s.status;
+          q[20] = (uint32_t)s.trials; q[21] = (uint32_t)s.fails;
+          q[22] = (uint32_t)idx; q[23] = fresh ? 1u : 0u;
+          q[24] = (uint32_t)(sl.base - slot0);               // the shared-memory column that holds U, X, obstacles
+        }
+        __syncthreads();
+        active = (int)threadIdx.x < n_active;
+        fresh = false;
+        if (active) {
+          const uint32_t* q = scratch + threadIdx.x * kCompactWords;
+          p.x0 = __hiloint2double((int)q[1], (int)q[0]); p.y0 = __hiloint2double((int)q[3], (int)q[2]);
+          p.ego_index = (int)q[4]; p.n_obs = (int)q[5]; p.is_collide = (int)q[6];
+          p.w_speed = __uint_as_float(q[7]); p.w_control = __uint_as_float(q[8]); p.w_diff = __uint_as_float(q[9]);
+          p.vr_a = __uint_as_float(q[10]); p.vr_slope = __uint_as_float(q[11]); p.vr_b = __uint_as_float(q[12]);
+          p.vr_n = (int)q[13];
+          s.J = __uint_as_float(q[14]); s.mu = __uint_as_float(q[15]);
+          s.J_mark = __uint_as_float(q[17]); s.iter = (int)q[18]; s.status = (int)q[19];
+          s.trials = (int)q[20]; s.fails = (int)q[21]; s.done = false;
+          idx = (int)q[22]; fresh = q[23] != 0u;
+          sl.base = slot0 + q[24];
+        }
+        live_warps = (n_active + 31) >> 5;
+        __syncthreads();                                     // scratch may be rewritten by the next compaction
+      }
+      if (warp >= live_warps) continue;                      // parked: nothing to sweep, back to the barrier
+    } else {
+      if (!__any_sync(full, active)) break;
+    }
     float d1 = 0.f, d2 = 0.f, alpha = 1.f, Jn = 0.f, md = 0.f;
     bool acc = false;
     const bool run = active && !fresh;
@@ -246,18 +308,10 @@ k_solve_tmem(const SolverConfig cfg, const MpcProblemBatch batch, const MpcSolve
     if (any_run) {                                          // all 32 lanes sweep; only `run` lanes keep the result
       backward_pass(cfg, p, ref, sl, s.mu, s.hs, &d1, &d2);
       __syncwarp();
-    }
-#if MPC_BLOCK_SYNC >= 2
-    __syncthreads();
-#endif
-    if (any_run) {
       const bool ok = line_search_pass(cfg, p, ref, sl, s, d1, d2, alpha, Jn, md);
       acc = run && ok;
       __syncwarp();
     }
-#if MPC_BLOCK_SYNC >= 3
-    __syncthreads();
-#endif
     const bool do_commit = active && (fresh || acc);
     if (__any_sync(full, do_commit)) {
       float Jc, mdc;
@@ -285,7 +339,7 @@ k_solve_tmem(const SolverConfig cfg, const MpcProblemBatch batch, const MpcSolve
               out.U[((size_t)idx * cfg.N + k) * 2 + 1] = sl.U(k, 1);
             }
           active = false;
-          need_fetch = true;
+          need_fetch = !drained;                             // nothing left to fetch once a lane of the block saw the queue empty
         }
       }
     }
