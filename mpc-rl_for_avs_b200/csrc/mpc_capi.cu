@@ -120,15 +120,16 @@ MPC_API int mpc_create(const MpcConfig* cfg, int device, int max_batch, MpcHandl
   } while (0)
 
   CKC(cudaSetDevice(device));
-  // grid / block: as many problems resident per SM as the on-chip storage allows.  Default: gains in
-  // tensor memory (352 problems / SM at H=20, M=8); MPC_USE_TMEM=0 or a horizon whose gains do not fit the
-  // 512 TMEM columns selects the shared-memory kernel (192 problems / SM).
+  // grid / block.  Default: gains in tensor memory, at most 256 problems (8 warps, two per scheduler) per SM --
+  // up to 352 fit at H=20, M=8 and can be forced with threads_per_block, but measured no faster even at 1 M
+  // problems per launch; MPC_USE_TMEM=0 or a horizon whose gains do not fit the 512 TMEM columns selects
+  // the shared-memory kernel (192 problems / SM).
   const char* env_tmem = getenv("MPC_USE_TMEM");
   int want_tmem = env_tmem ? atoi(env_tmem) : 1;
   int tpb = 0;
   if (want_tmem) {
     static const int cand[] = {384, 352, 320, 288, 256, 192, 128};
-    const int cap = cfg->threads_per_block > 0 ? cfg->threads_per_block : 384;
+    const int cap = cfg->threads_per_block > 0 ? cfg->threads_per_block : 256;   // 256 is as fast as 352 at 1 M problems and faster below
     for (int c : cand) {
       if (c > cap) continue;
       if (!tmem_layout_fits(N, c)) continue;
@@ -272,7 +273,6 @@ static void pick_solve_launch(const MpcHandle* h, int B, SolveLaunch& s) {
     if (want < h->tpb) { s.threads_per_block = want; s.smem_bytes = solve_smem_bytes(N, M, want); }
     return;
   }
-  if (B >= 500000) return;                                   // throughput bound: the largest block
   if (want <= 96 && solve_smem_bytes(N, M, want) <= (size_t)h->smem_optin) {
     s.use_tmem = 0; s.threads_per_block = want; s.smem_bytes = solve_smem_bytes(N, M, want);
     return;
