@@ -14,6 +14,8 @@ using namespace mpcb;
 
 static thread_local std::string g_create_error;
 
+constexpr int kHostChunks = 4;      // pieces of the observation upload in mpc_predict_host
+
 struct MpcHandle {
   MpcConfig cfg;
   SolverConfig scfg;
@@ -37,6 +39,8 @@ struct MpcHandle {
   float* d_actions = nullptr; int32_t* d_status = nullptr; int32_t* d_iters = nullptr; float* d_cost = nullptr;
   int32_t* d_mem = nullptr; int32_t* d_memo = nullptr; uint8_t* d_iscol = nullptr;
   cudaStream_t host_stream = nullptr;
+  cudaStream_t copy_stream = nullptr;        // uploads of mpc_predict_host
+  cudaEvent_t copy_done[kHostChunks] = {};
   // measurement
   int64_t launches = 0;
   bool timing = false;
@@ -74,6 +78,8 @@ MPC_API int mpc_destroy(MpcHandle* h) {
   cudaFree(h->d_actions); cudaFree(h->d_status); cudaFree(h->d_iters); cudaFree(h->d_cost);
   cudaFree(h->d_mem); cudaFree(h->d_memo); cudaFree(h->d_iscol);
   if (h->host_stream) cudaStreamDestroy(h->host_stream);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  for (auto e : h->copy_done) if (e) cudaEventDestroy(e);
   delete h;
   return MPC_OK;
 }
@@ -197,6 +203,8 @@ MPC_API int mpc_create(const MpcConfig* cfg, int device, int max_batch, MpcHandl
   CKC(cudaMemset(h->d_memo, 0xff, B * 4));
   CKC(cudaMemset(h->d_iscol, 0, B));
   CKC(cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking));
+  CKC(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  for (int c = 0; c < kHostChunks; ++c) CKC(cudaEventCreateWithFlags(&h->copy_done[c], cudaEventDisableTiming));
   CKC(cudaDeviceSynchronize());
 #undef CKC
   *out = h;
@@ -312,6 +320,25 @@ MPC_API int mpc_solve(MpcHandle* h, const MpcProblemBatch* batch, int B, const M
   return MPC_OK;
 }
 
+// launches k_prepare for environments [first, first + count) of a call of B environments
+static int prepare_range(MpcHandle* h, const float* obs, const float* ref_speed, const float* weights, const uint8_t* reset_mask,
+                         const MpcLatchState* latch, int B, int first, int count, const MpcCollisionOut* col, cudaStream_t st) {
+  PrepareParams p{};
+  p.obs = obs; p.ref_speed = ref_speed; p.weights = weights; p.reset_mask = reset_mask;
+  if (latch) p.latch = *latch;
+  if (col) p.col = *col;
+  p.ws = h->ws;
+  p.B = B; p.first = first; p.count = count;
+  p.V = h->cfg.vehicles_count; p.M = h->scfg.M; p.N = h->scfg.N;
+  // dt arrives as float (0.1f); the reference's dt is the double 1/policy_frequency
+  p.dt = 1.0 / (double)(long long)(1.0 / (double)h->cfg.dt + 0.5) ;
+  p.w_speed = h->cfg.weight_speed; p.w_control = h->cfg.weight_control; p.w_diff = h->cfg.weight_input_diff;
+  p.collision_check = h->cfg.collision_check;
+  CK(h, launch_prepare(p, st));
+  h->launches += 1;
+  return MPC_OK;
+}
+
 MPC_API int mpc_prepare(MpcHandle* h, const float* obs, const float* ref_speed, const float* weights, const uint8_t* reset_mask,
                 const MpcLatchState* latch, int B, const MpcCollisionOut* col, void* stream) {
   if (!h) return MPC_ERR_BAD_ARG;
@@ -320,24 +347,12 @@ MPC_API int mpc_prepare(MpcHandle* h, const float* obs, const float* ref_speed, 
   if (B > h->max_batch) return fail(h, MPC_ERR_TOO_LARGE, "mpc_prepare: B exceeds max_batch of mpc_create");
   if (h->cfg.collision_check && (!latch || !latch->collision_memory || !latch->memo_conflict || !latch->is_collide))
     return fail(h, MPC_ERR_BAD_ARG, "mpc_prepare: latch state is required when collision_check is on");
-  if (B == 0) return MPC_OK;
   cudaStream_t st = (cudaStream_t)stream;
   CK(h, cudaSetDevice(h->device));
-  PrepareParams p{};
-  p.obs = obs; p.ref_speed = ref_speed; p.weights = weights; p.reset_mask = reset_mask;
-  if (latch) p.latch = *latch;
-  if (col) p.col = *col;
-  p.ws = h->ws;
-  p.B = B; p.V = h->cfg.vehicles_count; p.M = h->scfg.M; p.N = h->scfg.N;
-  // dt arrives as float (0.1f); the reference's dt is the double 1/policy_frequency
-  p.dt = 1.0 / (double)(long long)(1.0 / (double)h->cfg.dt + 0.5) ;
-  p.w_speed = h->cfg.weight_speed; p.w_control = h->cfg.weight_control; p.w_diff = h->cfg.weight_input_diff;
-  p.collision_check = h->cfg.collision_check;
   int rc;
   if ((rc = timed_begin(h, h->ev_prepare, st))) return rc;
-  CK(h, launch_prepare(p, st));
+  if ((rc = prepare_range(h, obs, ref_speed, weights, reset_mask, latch, B, 0, B, col, st))) return rc;
   if ((rc = timed_end(h, h->ev_prepare, st))) return rc;
-  h->launches += 1;
   return MPC_OK;
 }
 
@@ -361,17 +376,36 @@ MPC_API int mpc_predict_host(MpcHandle* h, const float* obs_host, const float* r
   CK(h, cudaSetDevice(h->device));
   cudaStream_t st = h->host_stream;
   int64_t up = 0, down = 0;
-  const size_t nobs = (size_t)B * h->cfg.vehicles_count * 8 * 4;
-  CK(h, cudaMemcpyAsync(h->d_obs, obs_host, nobs, cudaMemcpyHostToDevice, st)); up += nobs;
-  if (ref_speed_host) { CK(h, cudaMemcpyAsync(h->d_ref_speed, ref_speed_host, (size_t)B * 4, cudaMemcpyHostToDevice, st)); up += (int64_t)B * 4; }
-  if (weights_host) { CK(h, cudaMemcpyAsync(h->d_weights, weights_host, (size_t)B * 12, cudaMemcpyHostToDevice, st)); up += (int64_t)B * 12; }
-  if (reset_mask_host) { CK(h, cudaMemcpyAsync(h->d_reset, reset_mask_host, (size_t)B, cudaMemcpyHostToDevice, st)); up += B; }
+  const size_t row = (size_t)h->cfg.vehicles_count * 8 * 4;
   MpcLatchState latch{h->d_mem, h->d_memo, h->d_iscol};
   MpcSolveOut out{h->d_actions, h->d_status, h->d_iters, h->d_cost, nullptr};
   MpcCollisionOut col{};
-  int rc = mpc_predict(h, h->d_obs, ref_speed_host ? h->d_ref_speed : nullptr, weights_host ? h->d_weights : nullptr,
-                       reset_mask_host ? h->d_reset : nullptr, &latch, B, &out, &col, st);
-  if (rc) return rc;
+  const float* d_rs = ref_speed_host ? h->d_ref_speed : nullptr;
+  const float* d_w = weights_host ? h->d_weights : nullptr;
+  const uint8_t* d_rm = reset_mask_host ? h->d_reset : nullptr;
+  int rc;
+  // The observations are 97 % of the upload.  They go up in kHostChunks pieces on a second stream and
+  // k_prepare (independent per environment) starts on each piece as soon as it has landed, so the copy of
+  // piece c+1 overlaps the parsing / collision logic of piece c.  Small batches take one piece.
+  const int chunks = B >= 8192 ? kHostChunks : 1;
+  if (ref_speed_host) { CK(h, cudaMemcpyAsync(h->d_ref_speed, ref_speed_host, (size_t)B * 4, cudaMemcpyHostToDevice, h->copy_stream)); up += (int64_t)B * 4; }
+  if (weights_host) { CK(h, cudaMemcpyAsync(h->d_weights, weights_host, (size_t)B * 12, cudaMemcpyHostToDevice, h->copy_stream)); up += (int64_t)B * 12; }
+  if (reset_mask_host) { CK(h, cudaMemcpyAsync(h->d_reset, reset_mask_host, (size_t)B, cudaMemcpyHostToDevice, h->copy_stream)); up += B; }
+  if ((rc = timed_begin(h, h->ev_prepare, st))) return rc;
+  for (int c = 0; c < chunks; ++c) {
+    const int lo = (int)((int64_t)B * c / chunks), hi = (int)((int64_t)B * (c + 1) / chunks);
+    if (hi <= lo) continue;
+    CK(h, cudaMemcpyAsync((char*)h->d_obs + (size_t)lo * row, (const char*)obs_host + (size_t)lo * row, (size_t)(hi - lo) * row,
+                          cudaMemcpyHostToDevice, h->copy_stream));
+    up += (int64_t)(hi - lo) * (int64_t)row;
+    CK(h, cudaEventRecord(h->copy_done[c], h->copy_stream));
+    CK(h, cudaStreamWaitEvent(st, h->copy_done[c], 0));
+    if ((rc = prepare_range(h, h->d_obs, d_rs, d_w, d_rm, &latch, B, lo, hi - lo, &col, st))) return rc;
+  }
+  if ((rc = timed_end(h, h->ev_prepare, st))) return rc;
+  MpcProblemBatch wb;
+  mpc_workspace_batch(h, &wb);
+  if ((rc = mpc_solve(h, &wb, B, &out, st))) return rc;
   CK(h, cudaMemcpyAsync(actions_host, h->d_actions, (size_t)B * 8, cudaMemcpyDeviceToHost, st)); down += (int64_t)B * 8;
   if (status_host) { CK(h, cudaMemcpyAsync(status_host, h->d_status, (size_t)B * 4, cudaMemcpyDeviceToHost, st)); down += (int64_t)B * 4; }
   if (is_collide_host) { CK(h, cudaMemcpyAsync(is_collide_host, h->ws.is_collide, (size_t)B, cudaMemcpyDeviceToHost, st)); down += B; }

@@ -32,7 +32,8 @@ struct PrepareParams {
   MpcLatchState latch;         // pointers may be null when collision_check == 0
   MpcCollisionOut col;         // any pointer may be null
   BatchWs ws;
-  int B, V, M, N;
+  int B, V, M, N;              // B = environments of the call = stride of the SoA outputs
+  int first, count;            // this launch handles environments [first, first + count)
   double dt;
   float w_speed, w_control, w_diff;
   int collision_check;

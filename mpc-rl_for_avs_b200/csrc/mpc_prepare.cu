@@ -59,9 +59,10 @@ k_prepare(const PrepareParams P) {
   __shared__ double s_ey[PPB][kPred + 1];
   const int g = threadIdx.x / LPP;                    // group inside the block
   const int l = threadIdx.x % LPP;                    // lane inside the group
-  const int b = blockIdx.x * PPB + g;
-  const bool live = b < P.B;
-  const int bb = live ? b : P.B - 1;                  // dead groups shadow the last env (no stores)
+  const int gi = blockIdx.x * PPB + g;
+  const bool live = gi < P.count;
+  const int b = P.first + gi;
+  const int bb = P.first + (live ? gi : P.count - 1); // dead groups shadow the last env (no stores)
   const unsigned gmask = (LPP == 32) ? 0xffffffffu : (((1u << LPP) - 1u) << ((threadIdx.x % 32) / LPP * LPP));
   const float* ob = P.obs + (size_t)bb * P.V * 8;
 
@@ -330,13 +331,13 @@ k_prepare(const PrepareParams P) {
 }
 
 cudaError_t launch_prepare(const PrepareParams& p, cudaStream_t stream) {
-  if (p.B <= 0) return cudaSuccess;
+  if (p.B <= 0 || p.count <= 0) return cudaSuccess;
   if (p.M <= 8) {
     const int ppb = 256 / 8;
-    k_prepare<8><<<(p.B + ppb - 1) / ppb, 256, 0, stream>>>(p);
+    k_prepare<8><<<(p.count + ppb - 1) / ppb, 256, 0, stream>>>(p);
   } else {
     const int ppb = 256 / 16;
-    k_prepare<16><<<(p.B + ppb - 1) / ppb, 256, 0, stream>>>(p);
+    k_prepare<16><<<(p.count + ppb - 1) / ppb, 256, 0, stream>>>(p);
   }
   return cudaGetLastError();
 }

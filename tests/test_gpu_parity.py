@@ -252,6 +252,19 @@ def test_predict_host_equals_predict_batch_and_is_deterministic(coll):
     assert np.array_equal(a1, a2)            # dynamic scheduling must not change results
     assert np.array_equal(a1, a3)
     assert up == g["obs"].nbytes and down == B * (8 + 4 + 1)
+    # large host batches upload the observations in pieces and parse each piece as it lands: same answer,
+    # also with pinned memory, a reference-speed column, a reset mask and a batch that does not divide evenly
+    Bl, M = 16389, 8
+    obs, rs, has = pkg.make_scenarios(Bl, M, seed=77)
+    rsn = np.where(has.numpy().reshape(-1), rs.numpy().reshape(-1), np.nan).astype(np.float32)
+    big = pkg.BatchedPureMPC(CFG, vehicles_count=M + 1, max_batch=Bl, collision_check=True, weight_distance=10.0)
+    ad = big.predict_batch(obs.cuda(), ref_speed=torch.from_numpy(rsn).cuda()).cpu().numpy()
+    st_d = big.status[:Bl].cpu().numpy()
+    for host_obs in (obs.numpy(), obs.pin_memory().numpy()):
+        ah, st_h, col_h, up, down = big.predict_host(host_obs, rsn, reset_mask=np.ones(Bl, np.uint8))
+        assert np.array_equal(ah, ad) and np.array_equal(st_h, st_d)
+        assert up == obs.numpy().nbytes + Bl * 4 + Bl and down == Bl * (8 + 4 + 1)
+        assert np.array_equal(col_h, big.is_collide[:Bl].cpu().numpy())
 
 
 def test_drop_in_agent_surface():
