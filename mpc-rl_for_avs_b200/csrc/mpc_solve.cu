@@ -189,6 +189,9 @@ bool tmem_layout_fits(int N, int tpb) {
 #ifndef MPC_COMPACT
 #define MPC_COMPACT 1
 #endif
+#ifndef MPC_SPEC
+#define MPC_SPEC 1
+#endif
 
 template <int TPB>
 __global__ void __launch_bounds__(TPB, 1)
@@ -215,6 +218,8 @@ k_solve_tmem(const SolverConfig cfg, const MpcProblemBatch batch, const MpcSolve
   uint32_t* const scratch = reinterpret_cast<uint32_t*>(slot0 + slots_per_problem_tmem(cfg.N, cfg.M) * TPB);
   int* const s_wcnt = reinterpret_cast<int*>(scratch + kCompactMax * kCompactWords);
   int live_warps = TPB / 32;                                // warps that may still hold problems (block-uniform)
+  constexpr bool kSpec = kCompact && (MPC_SPEC != 0);
+  int spec_k = 1, spec_j = 0;                               // lanes per problem (block-uniform) / this lane's index in its group
   bool drained = false;                                     // some lane of the block found the queue empty (block-uniform)
   bool saw_empty = false;                                   // this lane did
 
@@ -254,15 +259,26 @@ k_solve_tmem(const SolverConfig cfg, const MpcProblemBatch batch, const MpcSolve
       // but 56 us with one: packing the survivors into <= 4 (then 2, then 1) warps shortens every trip of
       // the tail.  A problem's state is 25 registers + its shared-memory column (re-pointed, not copied);
       // the gains in TMEM are rebuilt by the next backward sweep, so nothing else moves.
-      const int n_active = __syncthreads_count(active);
+      //
+      // Speculation (kSpec): when <= 64 (<= 32) problems are left, each gets 2 (4) adjacent lanes.  Lane j of a
+      // group runs the SAME trip with the damping the sequential algorithm would use after j rejected steps
+      // (mu -> max(30 mu, 3), X and U untouched by a rejection), so one trip decides up to 4 sequential trips:
+      // the first lane whose step is accepted wins, the rejections before it are replayed in the bookkeeping,
+      // the winner commits.  Same iterates, same iteration counts, same results -- fewer trips in the tail,
+      // where ~40 % of the trips of the slow problems are rejections.
+      const int n_active = __syncthreads_count(active && spec_j == 0);
       if (n_active == 0) break;
       if (!drained) drained = __syncthreads_or(saw_empty) != 0;     // every decision below is taken on barrier results only
-      if (drained && live_warps > 1 && n_active <= 16 * live_warps && n_active <= kCompactMax) {
-        const unsigned bal = __ballot_sync(full, active);
+      int k_new = (kSpec && drained) ? (n_active <= 32 ? 4 : (n_active <= 64 ? 2 : 1)) : 1;
+      if (k_new < spec_k) k_new = spec_k;
+      const int warps_new = (n_active * k_new + 31) >> 5;
+      if (drained && n_active <= kCompactMax && (k_new > spec_k || (live_warps > 1 && 2 * warps_new <= live_warps))) {
+        const bool lead = active && spec_j == 0;
+        const unsigned bal = __ballot_sync(full, lead);
         const int lane = threadIdx.x & 31;
         if (lane == 0) s_wcnt[warp] = __popc(bal);
         __syncthreads();
-        if (active) {
+        if (lead) {
           int r = __popc(bal & ((1u << lane) - 1u));
           for (int w = 0; w < warp; ++w) r += s_wcnt[w];
           uint32_t* q = scratch + r * kCompactWords;
@@ -279,10 +295,13 @@ k_solve_tmem(const SolverConfig cfg, const MpcProblemBatch batch, const MpcSolve
           q[24] = (uint32_t)(sl.base - slot0);               // the shared-memory column that holds U, X, obstacles
         }
         __syncthreads();
-        active = (int)threadIdx.x < n_active;
+        const int group = (int)threadIdx.x / k_new;
+        spec_k = k_new;
+        spec_j = (int)threadIdx.x % k_new;
+        active = group < n_active;
         fresh = false;
         if (active) {
-          const uint32_t* q = scratch + threadIdx.x * kCompactWords;
+          const uint32_t* q = scratch + group * kCompactWords;
           p.x0 = __hiloint2double((int)q[1], (int)q[0]); p.y0 = __hiloint2double((int)q[3], (int)q[2]);
           p.ego_index = (int)q[4]; p.n_obs = (int)q[5]; p.is_collide = (int)q[6];
           p.w_speed = __uint_as_float(q[7]); p.w_control = __uint_as_float(q[8]); p.w_diff = __uint_as_float(q[9]);
@@ -293,8 +312,10 @@ k_solve_tmem(const SolverConfig cfg, const MpcProblemBatch batch, const MpcSolve
           s.trials = (int)q[20]; s.fails = (int)q[21]; s.done = false;
           idx = (int)q[22]; fresh = q[23] != 0u;
           sl.base = slot0 + q[24];
+        } else {
+          spec_j = 0;                                        // idle lanes must not look like followers of a group
         }
-        live_warps = (n_active + 31) >> 5;
+        live_warps = warps_new;
         __syncthreads();                                     // scratch may be rewritten by the next compaction
       }
       if (warp >= live_warps) continue;                      // parked: nothing to sweep, back to the barrier
@@ -302,30 +323,53 @@ k_solve_tmem(const SolverConfig cfg, const MpcProblemBatch batch, const MpcSolve
       if (!__any_sync(full, active)) break;
     }
     float d1 = 0.f, d2 = 0.f, alpha = 1.f, Jn = 0.f, md = 0.f;
-    bool acc = false;
+    bool ok = false;
     const bool run = active && !fresh;
     const bool any_run = __any_sync(full, run);
+    const int trials0 = s.trials;
     if (any_run) {                                          // all 32 lanes sweep; only `run` lanes keep the result
-      backward_pass(cfg, p, ref, sl, s.mu, s.hs, &d1, &d2);
+      float mu_j = s.mu;
+      if (kSpec) for (int i = 0; i < spec_j; ++i) mu_j = max_(mu_j * 30.f, 3.f);   // damping after i rejected steps (after_line_search)
+      backward_pass(cfg, p, ref, sl, mu_j, s.hs, &d1, &d2);
       __syncwarp();
-      const bool ok = line_search_pass(cfg, p, ref, sl, s, d1, d2, alpha, Jn, md);
-      acc = run && ok;
+      ok = line_search_pass(cfg, p, ref, sl, s, d1, d2, alpha, Jn, md) && run;
       __syncwarp();
     }
-    const bool do_commit = active && (fresh || acc);
+    // ---- bookkeeping of the solver state (before the commit sweep: it only needs the line-search results)
+    bool commit_me = false;
+    if (!kSpec || spec_k == 1) {
+      if (run) { after_line_search(cfg, s, ok, alpha, Jn, md); commit_me = ok; }
+    } else {
+      const unsigned okmask = __ballot_sync(full, ok);
+      const int gbase = (threadIdx.x & 31) & ~(spec_k - 1);
+      const unsigned gm = (okmask >> gbase) & ((1u << spec_k) - 1u);
+      const int w = gm ? (__ffs((int)gm) - 1) : spec_k;     // first speculative lane whose step was accepted
+      const int src = gbase + (w < spec_k ? w : 0);
+      const float a_w = __shfl_sync(full, alpha, src), J_w = __shfl_sync(full, Jn, src), md_w = __shfl_sync(full, md, src);
+      if (run) {
+        int t = 0;
+        bool reached = false;
+        for (; t < spec_k && !s.done; ++t) {
+          if (t == w) { after_line_search(cfg, s, true, a_w, J_w, md_w); reached = true; ++t; break; }
+          after_line_search(cfg, s, false, 1.f, 0.f, 0.f);
+        }
+        s.trials = trials0 + MPC_LS_NA * t;
+        commit_me = reached && spec_j == w;
+      }
+    }
+    const bool do_commit = active && (fresh ? spec_j == 0 : commit_me);
+    float Jc = 0.f, mdc = 0.f;
     if (__any_sync(full, do_commit)) {
-      float Jc, mdc;
       forward_pass<float, 1, SL>(cfg, p, ref, sl, &alpha, do_commit, fresh, fresh, &Jc, &mdc);
-      if (fresh) Jn = Jc;
       __syncwarp();
     }
+    if (kSpec && spec_k > 1) Jc = __shfl_sync(full, Jc, (threadIdx.x & 31) & ~(spec_k - 1));   // the group leader did the first rollout
     if (active) {
       if (fresh) {
-        solve_init_finish(s, Jn);
+        solve_init_finish(s, Jc);
         fresh = false;
-      } else {
-        after_line_search(cfg, s, acc, alpha, Jn, md);
-        if (s.done) {
+      } else if (s.done) {
+        if (spec_j == 0) {
           if (!(s.J == s.J)) s.status |= kStatusNaN;
           out.actions[2 * (size_t)idx] = sl.U(0, 0);
           out.actions[2 * (size_t)idx + 1] = sl.U(0, 1);
@@ -338,9 +382,10 @@ k_solve_tmem(const SolverConfig cfg, const MpcProblemBatch batch, const MpcSolve
               out.U[((size_t)idx * cfg.N + k) * 2] = sl.U(k, 0);
               out.U[((size_t)idx * cfg.N + k) * 2 + 1] = sl.U(k, 1);
             }
-          active = false;
-          need_fetch = !drained;                             // nothing left to fetch once a lane of the block saw the queue empty
         }
+        active = false;
+        spec_j = 0;
+        need_fetch = !drained;                               // nothing left to fetch once a lane of the block saw the queue empty
       }
     }
   }
