@@ -273,21 +273,33 @@ static int timed_end(MpcHandle* h, std::vector<cudaEvent_t>& v, cudaStream_t st)
 // (tests/test_gpu_parity.py::test_result_independent_of_batch_size).
 static void pick_solve_launch(const MpcHandle* h, int B, SolveLaunch& s) {
   s.threads_per_block = h->tpb; s.smem_bytes = h->smem; s.use_tmem = h->use_tmem;
-  if (h->tpb_forced) return;
   const int N = h->scfg.N, M = h->scfg.M;
   const int per_sm = (B + h->sm_count - 1) / h->sm_count;
   int want = (per_sm + 31) / 32 * 32;
-  if (!h->use_tmem) {
-    if (want < h->tpb) { s.threads_per_block = want; s.smem_bytes = solve_smem_bytes(N, M, want); }
-    return;
+  static const int small_policy = getenv("MPC_SMALL_POLICY") ? atoi(getenv("MPC_SMALL_POLICY")) : 1;   // experiments: 0 = block ~ problems/SM
+  if (!h->tpb_forced) {
+    if (!h->use_tmem) {
+      if (want < h->tpb) { s.threads_per_block = want; s.smem_bytes = solve_smem_bytes(N, M, want); }
+    } else if (small_policy == 0) {
+      if (want <= 96 && solve_smem_bytes(N, M, want) <= (size_t)h->smem_optin) {
+        s.use_tmem = 0; s.threads_per_block = want; s.smem_bytes = solve_smem_bytes(N, M, want);
+      } else {
+        int tpb = want <= 128 ? 128 : (want <= 192 ? 192 : 256);
+        if (tpb > h->tpb_small) tpb = h->tpb_small;
+        s.threads_per_block = tpb; s.smem_bytes = solve_smem_bytes_tmem(N, M, tpb);
+      }
+    } else {
+      // the 192/256-thread TMEM kernel at every size: a block that gets fewer problems than lanes packs them
+      // into its lowest warps on the first trip and gives each 2-8 lanes to speculate with
+      int tpb = (want > 128 && want <= 192) ? 192 : 256;
+      if (tpb > h->tpb_small) tpb = h->tpb_small;
+      s.threads_per_block = tpb; s.smem_bytes = solve_smem_bytes_tmem(N, M, tpb);
+    }
   }
-  if (want <= 96 && solve_smem_bytes(N, M, want) <= (size_t)h->smem_optin) {
-    s.use_tmem = 0; s.threads_per_block = want; s.smem_bytes = solve_smem_bytes(N, M, want);
-    return;
-  }
-  int tpb = want <= 128 ? 128 : (want <= 192 ? 192 : 256);
-  if (tpb > h->tpb_small) tpb = h->tpb_small;
-  s.threads_per_block = tpb; s.smem_bytes = solve_smem_bytes_tmem(N, M, tpb);
+  // grid: one block per SM; small launches still spread over all SMs (>= 8 problems per block)
+  int need = (B + s.threads_per_block - 1) / s.threads_per_block;
+  if (s.use_tmem && small_policy != 0) { const int spread = (B + 7) / 8; if (spread > need) need = spread; }
+  s.grid = need < h->grid ? need : h->grid;
 }
 
 MPC_API int mpc_solve_config(const MpcHandle* h, int B, int* gains_in_tmem, int* threads_per_block) {
@@ -311,8 +323,6 @@ MPC_API int mpc_solve(MpcHandle* h, const MpcProblemBatch* batch, int B, const M
   s.cfg = h->scfg; s.batch = *batch; s.out = *out; s.B = B; s.work_counter = h->work_counter;
   s.u_init = h->u_init;
   pick_solve_launch(h, B, s);
-  int need = (B + s.threads_per_block - 1) / s.threads_per_block;
-  s.grid = need < h->grid ? need : h->grid;
   if ((rc = timed_begin(h, h->ev_solve, st))) return rc;
   CK(h, s.use_tmem ? launch_solve_tmem(s, st) : launch_solve(s, st));
   if ((rc = timed_end(h, h->ev_solve, st))) return rc;

@@ -192,6 +192,12 @@ bool tmem_layout_fits(int N, int tpb) {
 #ifndef MPC_SPEC
 #define MPC_SPEC 1
 #endif
+#ifndef MPC_SPEC_LANES
+#define MPC_SPEC_LANES 128     // lanes the speculating groups may occupy: 4 warps = one per scheduler
+#endif
+#ifndef MPC_SPEC_MAXK
+#define MPC_SPEC_MAXK 8
+#endif
 
 template <int TPB>
 __global__ void __launch_bounds__(TPB, 1)
@@ -229,12 +235,15 @@ k_solve_tmem(const SolverConfig cfg, const MpcProblemBatch batch, const MpcSolve
   SolveState<float> s;
   s.J = 0.f; s.mu = 0.f; s.hs = 1.f; s.J_mark = 0.f; s.iter = 0; s.status = 0; s.trials = 0; s.fails = 0; s.done = true;
   int idx = -1;
-  bool active = false, fresh = false, need_fetch = true;
+  bool active = false, fresh = false, need_fetch = true, first_wave = true;
 
   for (;;) {
     if (need_fetch) {
       need_fetch = false;
-      idx = atomicAdd(work_counter, 1);
+      // first wave: a static, evenly spread assignment (problem b + grid * t to thread t of block b) -- no storm of
+      // atomics on one counter, and a small launch lands in the lowest lanes of every block; later: the shared queue
+      idx = first_wave ? (int)(blockIdx.x + gridDim.x * threadIdx.x) : (int)(gridDim.x * TPB) + atomicAdd(work_counter, 1);
+      first_wave = false;
       active = idx < B;
       if (active) {
         load_problem(batch, B, idx, cfg, p, sl);
@@ -269,7 +278,10 @@ k_solve_tmem(const SolverConfig cfg, const MpcProblemBatch batch, const MpcSolve
       const int n_active = __syncthreads_count(active && spec_j == 0);
       if (n_active == 0) break;
       if (!drained) drained = __syncthreads_or(saw_empty) != 0;     // every decision below is taken on barrier results only
-      int k_new = (kSpec && drained) ? (n_active <= 32 ? 4 : (n_active <= 64 ? 2 : 1)) : 1;
+      int k_new = 1;
+      if (kSpec && drained) {                                // largest power of two with n_active * k <= MPC_SPEC_LANES, at most MPC_SPEC_MAXK
+        while (2 * k_new <= MPC_SPEC_MAXK && n_active * 2 * k_new <= MPC_SPEC_LANES) k_new *= 2;
+      }
       if (k_new < spec_k) k_new = spec_k;
       const int warps_new = (n_active * k_new + 31) >> 5;
       if (drained && n_active <= kCompactMax && (k_new > spec_k || (live_warps > 1 && 2 * warps_new <= live_warps))) {

@@ -324,11 +324,13 @@ def test_full_size_properties():
 
 
 def test_result_independent_of_batch_size():
-    """The library picks kernel (gains in shared or tensor memory) and block size from the launch size;
-    a problem's result must not depend on that choice: bit-identical actions, status and iteration counts."""
+    """The library picks block size and grid from the launch size, packs the survivors of a launch into few warps
+    and lets idle lanes speculate on the next damping values; forced block sizes select the other kernels (gains in
+    shared memory, TMEM kernel without compaction).  A problem's result must not depend on any of it:
+    bit-identical actions, status and iteration counts."""
     pkg = _pkg()
     M = 8
-    sizes = [65536, 40, 4096, 9000, 14000, 18000, 28000]
+    sizes = [65536, 40, 300, 4096, 9000, 14000, 18000, 28000]
     obs, rs, has = pkg.make_scenarios(max(sizes), M, seed=99)
     rs_dev = torch.where(has.reshape(-1, 1), rs, torch.full_like(rs, float("nan"))).cuda()
     obs_d = obs.cuda()
@@ -346,7 +348,18 @@ def test_result_independent_of_batch_size():
             continue
         assert torch.equal(a, ref[0][:B]), (B, sc)
         assert torch.equal(st, ref[1][:B]) and torch.equal(it, ref[2][:B]), (B, sc)
-    assert len(seen) >= 4          # both kernels and several block sizes were exercised
+    # the other kernels, forced: shared-memory gains (32 / 96 threads), TMEM without compaction (128, 352)
+    Bf = 20000
+    for tpb in (32, 96, 128, 352):
+        forced = pkg.BatchedPureMPC(CFG, vehicles_count=M + 1, max_batch=Bf, collision_check=True, weight_distance=10.0,
+                                    threads_per_block=tpb)
+        a = forced.predict_batch(obs_d[:Bf].contiguous(), ref_speed=rs_dev[:Bf].contiguous())
+        sc = forced.solve_config(Bf)
+        seen.add((sc["gains_in_tmem"], sc["threads_per_block"]))
+        assert sc["threads_per_block"] == tpb and sc["gains_in_tmem"] == (tpb >= 128)
+        assert torch.equal(a, ref[0][:Bf]), sc
+        assert torch.equal(forced.status[:Bf], ref[1][:Bf]) and torch.equal(forced.iters[:Bf], ref[2][:Bf]), sc
+    assert len(seen) >= 5
 
 
 def test_actions_written_into_a_bound_buffer():
