@@ -190,6 +190,35 @@ MPC_API int mpc_solve_config(const MpcHandle* h, int B, int* gains_in_tmem, int*
 /* device properties used for grid sizing */
 MPC_API int mpc_device_info(const MpcHandle* h, int* sm_count, int* cc_major, int* cc_minor, int* smem_per_block_optin);
 
+/* ---- SURVEY 8-f row N1 (not part of the MPC hot path): one step of the batched synthetic intersection
+ * environment of mpc_rl_for_avs_b200.rl as a single kernel.  Replaces nothing in the reference (highway-env's
+ * IntersectionEnv.step is third-party Python); rules cited in rl.py (envs/intersection_env__.py:61-129, :395-446).
+ * State arrays are updated in place; finished environments are reset in place.  The caller advances
+ * *counter by 10 draw steps afterwards (rl.BatchedIntersectionEnv does). */
+typedef struct MpcEnvStep {
+  float* ego;                 /* [B][4]  x, y, heading, speed                 in/out */
+  float* others;              /* [B][M][4]  x, y, speed, heading              in/out */
+  int32_t* t;                 /* [B]  policy steps since reset                in/out */
+  uint8_t* crashed_state;     /* [B]                                          out    */
+  const int64_t* counter;     /* device scalar: draw counter of the env's random numbers */
+  const float* action;        /* [B][2]  (accel, steer) as sent by the caller */
+  float* obs;                 /* [B][M+1][8]  observation after the step / reset */
+  float* terminal_obs;        /* [B][M+1][8]  observation before the reset       */
+  float* reward;              /* [B] */
+  uint8_t* done;              /* [B] */
+  uint8_t* crashed;           /* [B] */
+  uint8_t* arrived;           /* [B] */
+  uint8_t* truncated;         /* [B] */
+  float* speed;               /* [B]  ego speed after the step (before a reset) */
+  int32_t B, n_others;
+  int32_t substeps;           /* simulation_frequency / policy_frequency */
+  int32_t duration_steps;
+  int32_t raw_action;         /* 1: clip to [-1, 1] and scale to +-5 m/s^2, +-pi/4 (SB3 raw action path, quirk Q8) */
+  float dt_sim;
+  float arrive_x, arrive_y;   /* arrival test: x <= arrive_x and |y - arrive_y| < 4 */
+} MpcEnvStep;
+MPC_API int mpc_env_step(const MpcEnvStep* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,9 +53,18 @@ class MpcCollisionOut(C.Structure):
                 ("ego_index", C.c_void_p), ("stop_index", C.c_void_p), ("degenerate", C.c_void_p)]
 
 
+class MpcEnvStep(C.Structure):
+    _fields_ = [("ego", C.c_void_p), ("others", C.c_void_p), ("t", C.c_void_p), ("crashed_state", C.c_void_p),
+                ("counter", C.c_void_p), ("action", C.c_void_p), ("obs", C.c_void_p), ("terminal_obs", C.c_void_p),
+                ("reward", C.c_void_p), ("done", C.c_void_p), ("crashed", C.c_void_p), ("arrived", C.c_void_p),
+                ("truncated", C.c_void_p), ("speed", C.c_void_p), ("B", C.c_int32), ("n_others", C.c_int32),
+                ("substeps", C.c_int32), ("duration_steps", C.c_int32), ("raw_action", C.c_int32), ("dt_sim", C.c_float),
+                ("arrive_x", C.c_float), ("arrive_y", C.c_float)]
+
+
 EXPORTS = ["mpc_create", "mpc_destroy", "mpc_last_error", "mpc_workspace_batch", "mpc_rollout_cost", "mpc_solve",
            "mpc_prepare", "mpc_predict", "mpc_predict_host", "mpc_launch_count", "mpc_fp32_peak", "mpc_timing_begin",
-           "mpc_timing_end", "mpc_device_info", "mpc_set_warm_start", "mpc_solve_config"]
+           "mpc_timing_end", "mpc_device_info", "mpc_set_warm_start", "mpc_solve_config", "mpc_env_step"]
 
 
 class MpcError(RuntimeError):
@@ -108,6 +117,8 @@ def load() -> C.CDLL:
     lib.mpc_timing_end.restype = C.c_int
     lib.mpc_solve_config.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.mpc_solve_config.restype = C.c_int
+    lib.mpc_env_step.argtypes = [C.POINTER(MpcEnvStep), vp]
+    lib.mpc_env_step.restype = C.c_int
     lib.mpc_device_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.mpc_device_info.restype = C.c_int
     _lib = lib

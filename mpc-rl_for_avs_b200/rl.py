@@ -49,7 +49,8 @@ class BatchedIntersectionEnv:
     policy -> MPC -> env transition can be captured in a CUDA graph (`_MPCRollout(graph=True)`)."""
 
     def __init__(self, n_envs: int, n_others: int = 9, device="cuda", seed: int = 0, policy_frequency: int = 10,
-                 simulation_frequency: int = 30, duration_steps: int = 100, action_scaling: str = "sb3_raw"):
+                 simulation_frequency: int = 30, duration_steps: int = 100, action_scaling: str = "sb3_raw",
+                 fused: Optional[bool] = None):
         if action_scaling not in ("sb3_raw", "physical"):
             raise ValueError("action_scaling must be 'sb3_raw' or 'physical'")
         self.B, self.M, self.V = int(n_envs), int(n_others), int(n_others) + 1
@@ -60,6 +61,7 @@ class BatchedIntersectionEnv:
         self.action_scaling = action_scaling
         ref = torch.from_numpy(reference_path(1.0 / policy_frequency)).to(self.device)
         self.ref_xy = ref[:, :2].float()
+        self._arrive = (float(ref[-2, 0].float()), float(ref[-1, 1].float()))      # arrival test: x <= ref[-2].x, |y - ref[-1].y| < 4
         f = dict(device=self.device, dtype=torch.float32)
         self.ego = torch.zeros(self.B, 4, **f)               # x, y, heading, speed
         self.oth = torch.zeros(self.B, self.M, 4, **f)       # x, y, speed, heading
@@ -68,6 +70,15 @@ class BatchedIntersectionEnv:
         self._lane_heading = torch.tensor(_LANE_HEADING, **f)
         self._ctr = torch.full((1,), _i64(0x9E3779B97F4A7C15 * (2 * int(seed) + 1)), dtype=torch.int64, device=self.device)
         self._slot = torch.arange(self.B * 64, dtype=torch.int64, device=self.device).reshape(self.B, 64)
+        # fused=True: `step` is one CUDA kernel of libmpcb200 (csrc/mpc_env.cu: same rules, same random numbers);
+        # default on CUDA devices with <= 15 other vehicles.  The tensor program below is the specification and
+        # the CPU path.
+        self.fused = (self.device.type == "cuda" and self.M <= 15) if fused is None else bool(fused)
+        if self.fused:
+            if self.device.type != "cuda" or self.M > 15:
+                raise ValueError("the fused step needs a CUDA device and at most 15 other vehicles")
+            from . import _capi
+            self._capi, self._lib = _capi, _capi.load()
         self.reset()
 
     # ---------------------------------------------------------------------------------------------- random draws
@@ -133,6 +144,8 @@ class BatchedIntersectionEnv:
         """action [B, 2] = (accel, steer) as the caller sends it.  Returns (obs, reward, done, info); finished
         environments are reset in place (VecEnv semantics) and flagged in `done`; info["terminal_observation"]
         holds the observation before that reset (meaningful in the rows where `done`)."""
+        if self.fused:
+            return self._step_fused(action)
         a = action.to(self.device).float()
         if self.action_scaling == "sb3_raw":               # agents/a2c_mpc.py:151-153 -> ContinuousAction clip + lmap (quirk Q8)
             acc = a[:, 0].clamp(-1, 1) * 5.0
@@ -171,6 +184,35 @@ class BatchedIntersectionEnv:
                 "terminal_observation": self.observe()}
         obs = self.reset(done)
         return obs, reward, done, info
+
+
+def _fused_step(self, action: torch.Tensor):
+    """`step` as one launch of k_env_step (csrc/mpc_env.cu) on the current stream; no host synchronisation."""
+    C_ = self._capi.C
+    B, V, dev = self.B, self.V, self.device
+    a = action.to(device=dev, dtype=torch.float32).contiguous()
+    obs = torch.empty(B, V, 8, device=dev)
+    term = torch.empty(B, V, 8, device=dev)
+    reward = torch.empty(B, device=dev)
+    speed = torch.empty(B, device=dev)
+    flags = torch.empty(4, B, dtype=torch.bool, device=dev)              # done, crashed, arrived, truncated
+    args = self._capi.MpcEnvStep(
+        ego=self.ego.data_ptr(), others=self.oth.data_ptr(), t=self.t.data_ptr(), crashed_state=self.crashed.data_ptr(),
+        counter=self._ctr.data_ptr(), action=a.data_ptr(), obs=obs.data_ptr(), terminal_obs=term.data_ptr(),
+        reward=reward.data_ptr(), done=flags[0].data_ptr(), crashed=flags[1].data_ptr(), arrived=flags[2].data_ptr(),
+        truncated=flags[3].data_ptr(), speed=speed.data_ptr(), B=B, n_others=self.M, substeps=self.sub,
+        duration_steps=int(self.duration_steps), raw_action=int(self.action_scaling == "sb3_raw"), dt_sim=float(self.dt_sim),
+        arrive_x=self._arrive[0], arrive_y=self._arrive[1])
+    rc = self._lib.mpc_env_step(C_.byref(args), torch.cuda.current_stream(dev).cuda_stream)
+    if rc != 0:
+        raise RuntimeError(f"mpc_env_step failed with code {rc}")
+    self._ctr += _i64(10 * 0xD1B54A32D192ED03)                            # the ten draw calls of one step (spawn 4, reset 2 + 4)
+    self._keep = (a, obs, term)
+    info = {"crashed": flags[1], "arrived": flags[2], "truncated": flags[3], "speed": speed, "terminal_observation": term}
+    return obs, reward, flags[0], info
+
+
+BatchedIntersectionEnv._step_fused = _fused_step
 
 
 class _MlpExtractor(nn.Module):

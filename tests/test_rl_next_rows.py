@@ -195,3 +195,37 @@ def test_graph_captured_rollout_gpu():
         # the MPC really ran inside the graph: fresh iteration counts and bounded actions
         assert int(mpc.iters[:B].max()) > 0 and float(mpc.actions[:B, 0].abs().max()) <= 5.0 + 1e-5
         assert int(mpc.collision_memory[:B].max()) <= 10
+
+
+@pytest.mark.gpu
+def test_fused_env_step_matches_the_tensor_program_gpu():
+    """csrc/mpc_env.cu (one kernel per step) against the tensor program it restates: same seed, same actions ->
+    same events and the same random respawns; states agree to float rounding."""
+    from mpc_rl_for_avs_b200.rl import BatchedIntersectionEnv
+    B = 1024
+    a = BatchedIntersectionEnv(B, 9, device="cuda", seed=21, duration_steps=25, fused=True)
+    b = BatchedIntersectionEnv(B, 9, device="cuda", seed=21, duration_steps=25, fused=False)
+    assert a.fused and not b.fused and torch.equal(a.observe(), b.observe())
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    n_done = n_crash = n_arrive = 0
+    for step in range(60):
+        act = torch.rand(B, 2, generator=gen, device="cuda") * 2.4 - 1.2
+        act[:, 1] *= 0.2
+        if step == 10:                                           # put a few egos just before the end of the path: arrivals
+            for env in (a, b):
+                env.ego[:32, 0] = env.ref_xy[-2, 0] + 0.5
+                env.ego[:32, 1] = env.ref_xy[-1, 1]
+                env.ego[:32, 2] = -math.pi
+                env.ego[:32, 3] = 8.0
+        oa, ra, da, ia = a.step(act)
+        ob, rb, db, ib = b.step(act)
+        same = (da == db) & (ia["crashed"] == ib["crashed"]) & (ia["arrived"] == ib["arrived"])
+        assert float(same.float().mean()) > 0.999, step        # an event can flip only on a rounding tie (2.5 m / arrival line)
+        if not bool(same.all()):                                # re-synchronise the rare tie so the comparison can go on
+            b.ego.copy_(a.ego); b.oth.copy_(a.oth); b.t.copy_(a.t); ob = oa
+        assert torch.allclose(oa[same], ob[same], atol=2e-3, rtol=1e-4), step
+        assert torch.allclose(ra[same], rb[same], atol=1e-4) and torch.equal(ia["truncated"][same], ib["truncated"][same])
+        assert torch.allclose(ia["terminal_observation"][same], ib["terminal_observation"][same], atol=2e-3, rtol=1e-4)
+        assert torch.equal(a._ctr, b._ctr) and torch.equal(a.t[same], b.t[same])
+        n_done += int(da.sum()); n_crash += int(ia["crashed"].sum()); n_arrive += int(ia["arrived"].sum())
+    assert n_done > B and n_crash > 0 and n_arrive > 0          # resets, crashes and arrivals were all exercised
