@@ -61,6 +61,13 @@ k_prepare(const PrepareParams P) {
   constexpr int PPB = 256 / LPP;                      // environments per block
   __shared__ double s_ex[PPB][kPred + 1];
   __shared__ double s_ey[PPB][kPred + 1];
+  // the path table is indexed per lane (ego_index + idx, strided argmin): divergent __constant__ reads are
+  // serialised per distinct address, shared memory is not
+  __shared__ double s_ref[kNRef][4];
+  __shared__ double s_seg[kNRef - 1];
+  for (int i = threadIdx.x; i < kNRef * 4; i += blockDim.x) (&s_ref[0][0])[i] = (&c_refd[0][0])[i];
+  for (int i = threadIdx.x; i < kNRef - 1; i += blockDim.x) s_seg[i] = c_seg[i];
+  __syncthreads();
   const int g = threadIdx.x / LPP;                    // group inside the block
   const int l = threadIdx.x % LPP;                    // lane inside the group
   const int gi = blockIdx.x * PPB + g;
@@ -90,7 +97,7 @@ k_prepare(const PrepareParams P) {
   double bd = 1e300;
   int bj = 0;
   for (int j = l; j < kNRef; j += LPP) {
-    double d = dist2(ex - c_refd[j][0], ey - c_refd[j][1]);
+    double d = dist2(ex - s_ref[j][0], ey - s_ref[j][1]);
     if (d < bd) { bd = d; bj = j; }
   }
 #pragma unroll
@@ -134,7 +141,7 @@ k_prepare(const PrepareParams P) {
     const int len = kNRef - ego_index;                 // points of reference_trajectory[start:]
     int n_valid = 0;                                   // how many of t = 1..30 produce a point
     if (len >= 2) {
-      const double vref = c_refd[ego_index][2];
+      const double vref = s_ref[ego_index][2];
       // each lane owns the points t = 1 + l, 1 + l + LPP, ...; the speed ramp, the travelled distance and the
       // arc-length walk are all monotone in t, so they continue from the lane's previous point (same
       // sequential sums as the reference, evaluated once)
@@ -154,17 +161,17 @@ k_prepare(const PrepareParams P) {
           ++idx;
           if (idx >= len) break;
           prev = cum;
-          cum = cum + c_seg[ego_index + idx - 1];
+          cum = cum + s_seg[ego_index + idx - 1];
         }
         if (idx >= len) continue;                       // past the end of the path: no point
         double px, py;
-        if (idx == 0) { px = c_refd[ego_index][0]; py = c_refd[ego_index][1]; }
+        if (idx == 0) { px = s_ref[ego_index][0]; py = s_ref[ego_index][1]; }
         else {
           double alpha = (cum != prev) ? (dist - prev) / (cum - prev) : 1.0;
           alpha = alpha < 0.0 ? 0.0 : (alpha > 1.0 ? 1.0 : alpha);
-          const double ax = c_refd[ego_index + idx - 1][0], ay = c_refd[ego_index + idx - 1][1];
-          px = ax + alpha * (c_refd[ego_index + idx][0] - ax);
-          py = ay + alpha * (c_refd[ego_index + idx][1] - ay);
+          const double ax = s_ref[ego_index + idx - 1][0], ay = s_ref[ego_index + idx - 1][1];
+          px = ax + alpha * (s_ref[ego_index + idx][0] - ax);
+          py = ay + alpha * (s_ref[ego_index + idx][1] - ay);
         }
         s_ex[g][t] = px; s_ey[g][t] = py;
         ++n_valid;
@@ -238,7 +245,7 @@ k_prepare(const PrepareParams P) {
       if (have) {
         my_flag = 1;
         double bdr = 1e300;
-        for (int j = 0; j < kNRef; ++j) { double d = dist2(c_refd[j][0] - qx, c_refd[j][1] - qy); if (d < bdr) { bdr = d; my_cidx = j; } }
+        for (int j = 0; j < kNRef; ++j) { double d = dist2(s_ref[j][0] - qx, s_ref[j][1] - qy); if (d < bdr) { bdr = d; my_cidx = j; } }
       }
     }
   }
@@ -291,7 +298,7 @@ k_prepare(const PrepareParams P) {
   float w_s = P.w_speed, w_c = P.w_control, w_d = P.w_diff;
   if (P.weights) { w_s = P.weights[(size_t)b * 3]; w_c = P.weights[(size_t)b * 3 + 1]; w_d = P.weights[(size_t)b * 3 + 2]; }
   if (is_col) w_s = 100.f;                              // pure_mpc.py:143-147
-  float vr_a = 0.f, vr_slope = 0.f, vr_b = (float)c_refd[0][2];
+  float vr_a = 0.f, vr_slope = 0.f, vr_b = (float)s_ref[0][2];
   int vr_n = 0;
   bool override_v = false;
   if (P.ref_speed) {
