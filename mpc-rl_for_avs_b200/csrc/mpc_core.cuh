@@ -860,6 +860,16 @@ template <typename T> MPC_HD bool accept_step(T J, T Jn, T expected) {
 #ifndef MPC_LS_PASSES
 #define MPC_LS_PASSES 1
 #endif
+// Levenberg schedule: accepted step -> mu * MPC_MU_DEC (0 below 1e-3), rejected step -> max(mu * MPC_MU_INC, MPC_MU_MIN)
+#ifndef MPC_MU_DEC
+#define MPC_MU_DEC 0.1
+#endif
+#ifndef MPC_MU_INC
+#define MPC_MU_INC 30
+#endif
+#ifndef MPC_MU_MIN
+#define MPC_MU_MIN 3
+#endif
 constexpr int kLineSearchPasses = MPC_LS_PASSES;
 constexpr int kStallWindow = 6;        // iterations between progress checkpoints
 
@@ -871,10 +881,10 @@ MPC_HD void after_line_search(const SolverConfig& cfg, SolveState<T>& s, bool ac
     s.J = Jn;
     // a small step only proves stationarity when it is the un-damped Newton step
     if (alpha == T(1) && s.mu == T(0) && maxdu < T(cfg.tol_step)) s.done = true;
-    s.mu = s.mu > T(1e-3) ? s.mu * T(0.1) : T(0);
+    s.mu = s.mu > T(1e-3) ? s.mu * T(MPC_MU_DEC) : T(0);
   } else {
     s.fails++;
-    s.mu = max_(s.mu * T(30), T(3));
+    s.mu = max_(s.mu * T(MPC_MU_INC), T(MPC_MU_MIN));
     if (s.mu > T(1e9)) { s.status |= kStatusLineSearchFail; s.done = true; }
   }
   if (!s.done && s.iter % kStallWindow == 0) {

@@ -201,6 +201,11 @@ k_prepare(const PrepareParams P) {
         const double sc = (fabs(p2x - p1x) + fabs(p2y - p1y) + 1e-300) * (tlen + 1e-300);
         const double tol = 1e-7 * sc;
         if ((e0 > tol && e30 > tol) || (e0 < -tol && e30 < -tol)) continue;
+        // ... and the ego segment must straddle the track's line (most segments whose LINE the track crosses are
+        // nowhere near the track itself): same conservative band, the exact predicate below decides the rest
+        const double f1 = orient(Ox[0], Oy[0], Ox[kPred], Oy[kPred], p1x, p1y);
+        const double f2 = orient(Ox[0], Oy[0], Ox[kPred], Oy[kPred], p2x, p2y);
+        if ((f1 > tol && f2 > tol) || (f1 < -tol && f2 < -tol)) continue;
         int jlo = 0, jhi = kPred - 1;
         const double de = e30 - e0;
         if (fabs(de) > tol) {

@@ -341,7 +341,7 @@ k_solve_tmem(const SolverConfig cfg, const MpcProblemBatch batch, const MpcSolve
     const int trials0 = s.trials;
     if (any_run) {                                          // all 32 lanes sweep; only `run` lanes keep the result
       float mu_j = s.mu;
-      if (kSpec) for (int i = 0; i < spec_j; ++i) mu_j = max_(mu_j * 30.f, 3.f);   // damping after i rejected steps (after_line_search)
+      if (kSpec) for (int i = 0; i < spec_j; ++i) mu_j = max_(mu_j * float(MPC_MU_INC), float(MPC_MU_MIN));   // damping after i rejected steps (after_line_search)
       backward_pass(cfg, p, ref, sl, mu_j, s.hs, &d1, &d2);
       __syncwarp();
       ok = line_search_pass(cfg, p, ref, sl, s, d1, d2, alpha, Jn, md) && run;
