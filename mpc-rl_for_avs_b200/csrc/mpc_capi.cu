@@ -25,8 +25,7 @@ struct MpcHandle {
   int tpb = 0, grid = 0;
   size_t smem = 0;
   int use_tmem = 0;
-  int tpb_small = 0;              // TMEM kernel: block size used below kBigBatch problems per launch
-  size_t smem_small = 0;
+  int tpb_small = 0;              // TMEM kernel: largest block the per-launch choice may use (<= 256)
   bool tpb_forced = false;
   // device workspace
   void* ws_block = nullptr;       // one allocation carved into the BatchWs arrays
@@ -151,7 +150,6 @@ MPC_API int mpc_create(const MpcConfig* cfg, int device, int max_batch, MpcHandl
       // which grows with the number of resident warps; the largest block only pays off when throughput bound.
       h->tpb_forced = cfg->threads_per_block > 0;
       h->tpb_small = tpb < 256 ? tpb : 256;
-      h->smem_small = solve_smem_bytes_tmem(N, M, h->tpb_small);
     }
   }
   if (!h->use_tmem) {
@@ -167,7 +165,6 @@ MPC_API int mpc_create(const MpcConfig* cfg, int device, int max_batch, MpcHandl
   if (bps < 1) bps = 1;
   if (h->use_tmem) bps = 1;                                 // the CTA owns all 512 TMEM columns of its SM
   h->grid = h->sm_count * bps;
-  CKC(configure_solve_kernel(h->smem));
   CKC(upload_ref_table_solve());
   CKC(upload_ref_table_prepare());
 

@@ -57,7 +57,6 @@ struct SolveLaunch {
   size_t smem_bytes;
   int use_tmem;           // gains in tensor memory (k_solve_tmem) instead of shared memory (k_solve)
 };
-cudaError_t configure_solve_kernel(size_t smem_bytes);
 cudaError_t launch_solve(const SolveLaunch& s, cudaStream_t stream);
 cudaError_t launch_rollout_cost(const SolverConfig& cfg, const MpcProblemBatch& batch, int B, const float* U,
                                 float* X_out, float* cost6, float* total, cudaStream_t stream);

@@ -1,19 +1,23 @@
-// mpc_solve.cu -- the hot kernel: one persistent launch solves the whole batch of MPC problems.
+// mpc_solve.cu -- the hot kernels: one persistent launch solves the whole batch of MPC problems.
 //
-// Mapping (B200, 148 SMs, 227 KB shared memory / SM, 64 K registers / SM):
+// Mapping (B200, 148 SMs, 227 KB shared memory + 256 KB tensor memory / SM, 64 K registers / SM):
 //   * one problem per THREAD.  The horizon recursion (rollout, Riccati sweep) is serial in k and
 //     the per-stage blocks are 6x6 / 2x6 -- nothing a warp or a tensor core could share -- so the
 //     parallelism that exists is across problems and lanes stay full for the dominant work.
-//   * the per-problem horizon arrays (U, X, bf16-packed gains + feed-forward, obstacle tracks:
-//     296 words at H=20, M=8) live in a strided shared-memory slot file (slot*blockDim + tid: bank-conflict
-//     free), the value-function block (21+6 floats) in registers.  Shared memory, not registers,
-//     bounds residency: 192 problems / SM.
-//   * persistent grid (blocks = SMs x blocks/SM).  Iteration counts differ by 10x between
-//     problems, so a thread that finishes pulls the next problem index from a global counter
+//   * the per-problem horizon arrays U, X and the obstacle tracks (156 words at H=20, M=8) live in a
+//     strided shared-memory slot file (slot*blockDim + tid: bank-conflict free); the bf16-packed gains +
+//     feed-forward (140 words) live in TENSOR MEMORY in k_solve_tmem (this path issues no MMA, so TMEM is
+//     free capacity) and in the same slot file in k_solve; the value-function block (21+6 floats) in
+//     registers.
+//   * persistent grid, one block per SM.  Iteration counts differ by 10x between problems, so a thread
+//     that finishes pulls the next problem index from a global counter (after a static first wave)
 //     instead of idling until its warp's slowest problem ends.
-//   * line search is warp-synchronous: every lane runs the backward sweep, then lanes whose
-//     step was rejected retry with alpha/2 while the others wait; the commit sweep is shared.
-//   * HBM traffic is the compulsory ~0.3 KB per problem: this kernel is FP32-issue bound.
+//   * one trip of the loop = backward sweep, ONE line-search sweep of two candidates (alpha, alpha/4),
+//     commit sweep; a rejected step raises the Levenberg damping for the next trip.
+//   * the tail of a launch (k_solve_tmem, 192/256 threads): the surviving problems are packed into the
+//     lowest warps, and the freed lanes run the trips the sequential algorithm would run after 1, 2, ...
+//     rejections side by side (see the comments at kCompact / kSpec).
+//   * HBM traffic is the compulsory ~0.3 KB per problem: these kernels are FP32-issue / latency bound.
 #include "mpc_internal.h"
 
 #include "ref_table.inc"
@@ -172,7 +176,8 @@ k_solve(const SolverConfig cfg, const MpcProblemBatch batch, const MpcSolveOut o
 //   * every sweep is executed by all 32 lanes whenever ANY lane needs it.  Lanes without work compute on
 //     whatever their slots hold (finite loops only, results discarded); their TMEM stores land in their own
 //     cells.  Under SIMT those lanes were waiting anyway.
-//   * shared memory per problem is 156 words -> 352 problems resident per SM (192 with gains in shared memory).
+//   * shared memory per problem is 156 words -> up to 352 problems fit an SM (192 with gains in shared memory);
+//     256 are used, which leaves room for the scratch of the tail compaction.
 constexpr int kTmemColsPerStage = 8;
 // Tail compaction (k_solve_tmem, blocks of <= 256 threads): scratch for moving up to kCompactMax problems'
 // register state between lanes, plus one counter per warp.
@@ -441,8 +446,6 @@ template <int TPB> static cudaError_t launch_solve_t(const SolveLaunch& s, cudaS
   k_solve<TPB><<<s.grid, TPB, s.smem_bytes, stream>>>(s.cfg, s.batch, s.out, s.B, s.work_counter, s.u_init);
   return cudaGetLastError();
 }
-
-cudaError_t configure_solve_kernel(size_t) { return cudaSuccess; }
 
 cudaError_t launch_solve(const SolveLaunch& s, cudaStream_t stream) {
   switch (s.threads_per_block) {
