@@ -11,7 +11,8 @@ are GUI demos), and its two native dependencies are absent and not installable h
 ``casadi==3.6.6`` (SX graph + IPOPT/MUMPS; requirements.txt:4) and ``shapely==2.0.6`` (GEOS;
 requirements.txt:7).  What was done instead (tests/golden/make_reference_golden.py ->
 tests/golden/golden_reference.npz, checked by tests/test_reference_pin.py):
-the UNMODIFIED agents/pure_mpc.py and agents/archive/pure_mpc.py are imported from /root/reference
+the UNMODIFIED agents/pure_mpc.py, agents/pure_mpc_no_collision.py and agents/archive/pure_mpc.py are
+imported from /root/reference
 and executed with numeric stand-ins for casadi (numbers instead of symbols: every cost / constraint
 expression is evaluated by the reference's own lines at an injected trajectory) and shapely (textbook
 segment intersection).  Against those outputs this module is

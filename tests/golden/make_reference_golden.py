@@ -25,7 +25,8 @@ Outputs tests/golden/golden_reference.npz:
                                     computed: parsed ego state, ego_index, flags, conflict indices, memory,
                                     regenerated speed column, f, six components, max |g|, bounds, x0, action;
                                     plus the obstacle-distance component of agents/archive/pure_mpc.py:189-196
-                                    (the formula BASELINE config 3 adds) evaluated by that file at the same point
+                                    (the formula BASELINE config 3 adds) evaluated by that file at the same point,
+                                    and the literal objective of agents/pure_mpc_no_collision.py (BASELINE config 2)
   latch sequences                   the same agent object stepped through moving scenes
 The reference is never copied: it is imported from where it lies and only its outputs are stored.
 """
@@ -239,6 +240,7 @@ def main():
     sys.path.insert(0, REF)
     import agents.pure_mpc as ref_mpc                      # the reference, unmodified
     import agents.archive.pure_mpc as ref_archive          # the only version whose objective has the obstacle-distance term
+    import agents.pure_mpc_no_collision as ref_nocoll      # BASELINE config 2 names it; its objective omits the state cost (quirk Q3)
     import helpers
     from helpers import orc
     import mpc_rl_for_avs_b200 as pkg
@@ -280,11 +282,21 @@ def main():
         arch._solve()
         r["distance_component"] = CAPTURE["components"][4]
         r["archive_f"] = CAPTURE["f"]
+        # agents/pure_mpc_no_collision.py at the same (X, U): its literal objective (control + input_diff only), with the
+        # RL reference speed when the scene has one
+        nc = ref_nocoll.PureMPC_Agent(_Env(V), {"horizon": N, "render": False, "weight_speed": 1.0, "weight_control": 1.0,
+                                                "weight_input_diff": 1.0, "speed_override": None})
+        CAPTURE.clear()
+        nc.predict(obs_all[i], return_numpy=True, weights_from_RL=None,
+                   ref_speed=np.array([[rs_all[i]]], dtype=np.float32) if has_all[i] else None)
+        r["nocoll_f"] = CAPTURE["f"]
+        r["nocoll_gmax"] = float(np.max(np.abs(CAPTURE["g"])))
+        r["nocoll_ego_index"] = int(nc.ego_index)
         keep.append(i)
         rec.append(r)
     out = dict(obs=obs_all[keep], ref_speed=rs_all[keep], has_ref_speed=has_all[keep])
     for k in ("U", "X", "action", "f", "components", "g_max", "g0", "ref_v", "ego_index", "is_collide", "memory", "ego_state",
-              "distance_component", "archive_f"):
+              "distance_component", "archive_f", "nocoll_f", "nocoll_gmax", "nocoll_ego_index"):
         out["ss_" + k] = np.array([r[k] for r in rec])
     out["ss_flags"] = np.array([np.pad(r["flags"], (0, M - len(r["flags"]))) for r in rec])
     out["ss_cidx"] = np.array([np.pad(r["cidx"], (0, M - len(r["cidx"])), constant_values=-1) for r in rec])

@@ -2,7 +2,7 @@
 made by tests/golden/make_reference_golden.py: the unmodified agents/pure_mpc.py and agents/archive/pure_mpc.py
 run with numeric stand-ins for casadi / shapely).  What this pins: observation parsing, nearest path index,
 collision flags and conflict indices, the 10-step latch, reference-speed regeneration, the NLP's objective,
-components, dynamics constraints, bounds and cold start.  What it cannot pin: GEOS' intersection primitive
+components, dynamics constraints, bounds and cold start; the literal objective of agents/pure_mpc_no_collision.py.  What it cannot pin: GEOS' intersection primitive
 (stand-in) and IPOPT's choice of local optimum.
 
 Tolerances.  Discrete outputs: exact.  Continuous: the reference, under its pinned numpy 2.x, carries the ego
@@ -75,6 +75,19 @@ def test_oracle_single_step_against_reference():
         assert abs(comp[4] - G["ss_distance_component"][i]) <= 5e-4 * max(1.0, abs(G["ss_distance_component"][i])), i
 
 
+def test_oracle_literal_no_collision_objective_against_reference():
+    """agents/pure_mpc_no_collision.py (BASELINE config 2): its total cost is control + input_diff only (quirk Q3) and
+    depends on the observation only through the initial state, so the match is to machine precision."""
+    for i in range(S):
+        ag = orc.OraclePureMPCAgent(horizon=N, vehicles_count=V, collision_check=False, literal_no_collision=True)
+        rs = np.array([[G["ref_speed"][i]]]) if G["has_ref_speed"][i] else None
+        prob = ag.build_problem(orc.parse_obs(G["obs"][i], V), ref_speed=rs)
+        assert prob.ego_index == G["ss_nocoll_ego_index"][i]
+        J = orc.objective(G["ss_U"][i], prob)
+        assert abs(J - G["ss_nocoll_f"][i]) <= 1e-12 * max(1.0, abs(G["ss_nocoll_f"][i])), i
+    assert np.all(G["ss_nocoll_gmax"] <= 1e-6)
+
+
 def test_oracle_latch_sequences_against_reference():
     Q, T = G["seq_obs"].shape[:2]
     for q in range(Q):
@@ -122,6 +135,18 @@ def test_cuda_prepare_and_cost_against_reference():
     assert np.all(np.abs(tot - G["ss_f"]) <= 1e-5 * np.maximum(1.0, np.abs(G["ss_f"])))
     ref = G["ss_components"]
     assert np.all(np.abs(c6[:, :4] - ref[:, :4]) <= 1e-5 * np.maximum(1.0, np.abs(ref[:, :4])))
+
+
+@pytest.mark.gpu
+def test_cuda_literal_no_collision_objective_against_reference():
+    import mpc_rl_for_avs_b200 as pkg
+    agent = pkg.BatchedPureMPC(CFG, vehicles_count=V, max_batch=S, collision_check=False, literal_no_collision=True)
+    rs = np.where(G["has_ref_speed"], G["ref_speed"], np.nan).astype(np.float32)
+    ws = agent.prepare_batch(torch.from_numpy(G["obs"]).cuda(), ref_speed=torch.from_numpy(rs).cuda())
+    assert np.array_equal(ws["ego_index"].cpu().numpy(), G["ss_nocoll_ego_index"])
+    _, _, tot = agent.rollout_cost(ws, torch.from_numpy(G["ss_U"].astype(np.float32)).cuda())
+    tot = tot.cpu().numpy().astype(np.float64)
+    assert np.all(np.abs(tot - G["ss_nocoll_f"]) <= 1e-5 * np.maximum(1.0, np.abs(G["ss_nocoll_f"])))
 
 
 @pytest.mark.gpu
