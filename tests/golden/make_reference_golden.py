@@ -282,6 +282,16 @@ def main():
         arch._solve()
         r["distance_component"] = CAPTURE["components"][4]
         r["archive_f"] = CAPTURE["f"]
+        # the shipped agent again with RL-set weights (v1 agents: weights_from_RL [[speed, control, input_diff]],
+        # agents/pure_mpc.py:96-104) on a fresh agent object; is_collide still forces the speed weight to 100 (quirk Q9)
+        wrl = rng.uniform(0.1, 5.0, size=(1, 3))
+        agw = make_agent(ref_mpc, V, N)
+        INJECT["x"], INJECT["u"] = r["X"].T.copy(), U.T.copy()
+        CAPTURE.clear()
+        agw.predict(obs_all[i], return_numpy=True, weights_from_RL=wrl, ref_speed=None)
+        r["rl_weights"] = wrl[0].copy()
+        r["rl_weights_f"] = CAPTURE["f"]
+        INJECT["x"], INJECT["u"] = r["X"].T.copy(), U.T.copy()
         # agents/pure_mpc_no_collision.py at the same (X, U): its literal objective (control + input_diff only), with the
         # RL reference speed when the scene has one
         nc = ref_nocoll.PureMPC_Agent(_Env(V), {"horizon": N, "render": False, "weight_speed": 1.0, "weight_control": 1.0,
@@ -296,7 +306,8 @@ def main():
         rec.append(r)
     out = dict(obs=obs_all[keep], ref_speed=rs_all[keep], has_ref_speed=has_all[keep])
     for k in ("U", "X", "action", "f", "components", "g_max", "g0", "ref_v", "ego_index", "is_collide", "memory", "ego_state",
-              "distance_component", "archive_f", "nocoll_f", "nocoll_gmax", "nocoll_ego_index"):
+              "distance_component", "archive_f", "nocoll_f", "nocoll_gmax", "nocoll_ego_index",
+              "rl_weights", "rl_weights_f"):
         out["ss_" + k] = np.array([r[k] for r in rec])
     out["ss_flags"] = np.array([np.pad(r["flags"], (0, M - len(r["flags"]))) for r in rec])
     out["ss_cidx"] = np.array([np.pad(r["cidx"], (0, M - len(r["cidx"])), constant_values=-1) for r in rec])

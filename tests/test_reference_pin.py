@@ -88,6 +88,18 @@ def test_oracle_literal_no_collision_objective_against_reference():
     assert np.all(G["ss_nocoll_gmax"] <= 1e-6)
 
 
+def test_oracle_rl_weights_against_reference():
+    """weights_from_RL [[speed, control, input_diff]] (v1 agents, agents/pure_mpc.py:96-104); a detected collision still
+    forces the speed weight to 100 (quirk Q9)."""
+    for i in range(S):
+        ag = orc.OraclePureMPCAgent(horizon=N, vehicles_count=V, collision_check=True)
+        parsed = orc.parse_obs(G["obs"][i], V)
+        ag.check_collision(parsed)
+        prob = ag.build_problem(parsed, weights_from_RL=G["ss_rl_weights"][i][None, :])
+        J = orc.objective(G["ss_U"][i], prob)
+        assert abs(J - G["ss_rl_weights_f"][i]) <= 1e-6 * max(1.0, abs(G["ss_rl_weights_f"][i])), i
+
+
 def test_oracle_latch_sequences_against_reference():
     Q, T = G["seq_obs"].shape[:2]
     for q in range(Q):
@@ -135,6 +147,16 @@ def test_cuda_prepare_and_cost_against_reference():
     assert np.all(np.abs(tot - G["ss_f"]) <= 1e-5 * np.maximum(1.0, np.abs(G["ss_f"])))
     ref = G["ss_components"]
     assert np.all(np.abs(c6[:, :4] - ref[:, :4]) <= 1e-5 * np.maximum(1.0, np.abs(ref[:, :4])))
+
+
+@pytest.mark.gpu
+def test_cuda_rl_weights_against_reference():
+    import mpc_rl_for_avs_b200 as pkg
+    agent = pkg.BatchedPureMPC(CFG, vehicles_count=V, max_batch=S, collision_check=True)
+    ws = agent.prepare_batch(torch.from_numpy(G["obs"]).cuda(), weights=torch.from_numpy(G["ss_rl_weights"].astype(np.float32)).cuda())
+    _, _, tot = agent.rollout_cost(ws, torch.from_numpy(G["ss_U"].astype(np.float32)).cuda())
+    tot = tot.cpu().numpy().astype(np.float64)
+    assert np.all(np.abs(tot - G["ss_rl_weights_f"]) <= 1e-5 * np.maximum(1.0, np.abs(G["ss_rl_weights_f"])))
 
 
 @pytest.mark.gpu
