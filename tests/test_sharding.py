@@ -59,3 +59,47 @@ def test_all_gather_actions_world2_gloo(total):
     exp = np.stack([idx, -2 * idx], axis=1)
     for r in range(2):
         assert np.array_equal(got[r], exp)
+
+
+class _StubMPC:
+    def predict_batch(self, obs, ref_speed=None, weights=None, reset_mask=None):
+        a = torch.zeros(obs.shape[0], 2)
+        a[:, 0] = 0.2
+        return a
+
+
+def _rl_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mpc_rl_for_avs_b200.rl import A2CMPC, PPOMPC, BatchedIntersectionEnv
+    out = {}
+    for name, Algo, kw in (("a2c", A2CMPC, {}), ("ppo", PPOMPC, {"n_epochs": 2, "batch_size": 16})):
+        env = BatchedIntersectionEnv(8, 9, device="cpu", seed=100 + rank)          # each rank owns its own environments
+        algo = Algo(env, _StubMPC(), n_steps=4, seed=rank, **kw)                   # different seeds: rank 0's weights are broadcast
+        w0 = torch.cat([p.detach().flatten() for p in algo.policy.parameters()]).clone()
+        algo.train_step()
+        w1 = torch.cat([p.detach().flatten() for p in algo.policy.parameters()])
+        out[name] = (w0.numpy(), w1.numpy())
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_data_parallel_rl_update_world2_gloo():
+    """N2 over several ranks: environments are sharded, the policy is replicated (broadcast at start, gradients
+    all-reduced per step), so all ranks hold identical weights before and after an update on different rollouts."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + 77
+    procs = [ctx.Process(target=_rl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for name in ("a2c", "ppo"):
+        (a0, a1), (b0, b1) = got[0][name], got[1][name]
+        assert np.array_equal(a0, b0)                          # broadcast of rank 0's initial weights
+        assert np.allclose(a1, b1, rtol=0, atol=1e-7) and not np.array_equal(a0, a1)
