@@ -32,7 +32,7 @@ extern "C" {
 #define MPC_API
 #endif
 
-#define MPC_ABI_VERSION 1
+#define MPC_ABI_VERSION 2
 #define MPC_MAX_OBSTACLES 16
 #define MPC_N_REF 85 /* rows of the reference path, agents/base_agent.py:127-152 */
 
@@ -47,11 +47,15 @@ typedef enum MpcError {
 /* per-problem status bits written to MpcSolveOut.status
  * (the reference only prints on solver failure and still applies the iterate,
  *  agents/pure_mpc.py:303-305; here the caller gets the flag) */
-#define MPC_STATUS_CONVERGED 0
+#define MPC_STATUS_CONVERGED 0          /* un-damped Newton step below tol_step accepted: a certified local optimum */
 #define MPC_STATUS_MAX_ITER 1
 #define MPC_STATUS_LINESEARCH_FAIL 2
 #define MPC_STATUS_NAN 4
-#define MPC_STATUS_INFEASIBLE_START 8
+#define MPC_STATUS_INFEASIBLE_START 8   /* s0 violates a state bound: the reference NLP is infeasible */
+#define MPC_STATUS_STALLED 16           /* no progress over 6 iterations while the steps were still large */
+#define MPC_STATUS_KINK 32              /* settled (objective stationary to 1e-7 over 6 iterations, steps < 10 tol_step) on a
+                                         * kink of the bound-clamped dynamics; usually an optimum, not certified */
+#define MPC_MAX_STARTS 8
 
 /* Configuration = cfg["pure_mpc"] of the reference (config/cfg.yaml:88-106) plus the constants
  * that are hard-coded in agents/pure_mpc.py, and the solver's own knobs. */
@@ -72,6 +76,8 @@ typedef struct MpcConfig {
   float reg_min;              /* eigenvalue floor of the control Hessian */
   int32_t threads_per_block;  /* 0 = default */
   int32_t blocks_per_sm;      /* 0 = default */
+  int32_t n_starts;           /* start portfolio: solves per problem, lowest objective wins; 1 = only the reference's cold
+                               * start (zero controls, agents/pure_mpc.py:244); 0 = default (4); <= MPC_MAX_STARTS */
 } MpcConfig;
 
 /* One batch of parsed problems, SoA, length B (what _parse_obs + _check_collision +
@@ -100,7 +106,7 @@ typedef struct MpcProblemBatch {
 typedef struct MpcSolveOut {
   float* actions;             /* [B][2]  first control (accel, steer) */
   int32_t* status;            /* [B]     MPC_STATUS_* bits */
-  int32_t* iters;             /* [B]     iterations used */
+  int32_t* iters;             /* [B]     iterations used (total over the starts of the portfolio) */
   float* cost;                /* [B]     objective at the returned iterate (pure_mpc.py:204-212) */
   float* U;                   /* [B][N][2] full control sequence, or NULL */
 } MpcSolveOut;

@@ -6,9 +6,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, os.environ.get("MPC_LIB_NAME", "libmpcb200.so"))   # override only for A/B experiment builds
+LIB_PATH = os.path.join(_HERE, "libmpcb200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_OBSTACLES = 16
 N_REF = 85
 
@@ -17,6 +17,9 @@ STATUS_MAX_ITER = 1
 STATUS_LINESEARCH_FAIL = 2
 STATUS_NAN = 4
 STATUS_INFEASIBLE_START = 8
+STATUS_STALLED = 16
+STATUS_KINK = 32
+MAX_STARTS = 8
 
 ERR_BAD_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_TOO_LARGE = -1, -2, -3, -4
 
@@ -30,7 +33,8 @@ class MpcConfig(C.Structure):
                 ("weight_speed", C.c_float), ("weight_control", C.c_float), ("weight_input_diff", C.c_float),
                 ("weight_distance", C.c_float), ("weight_collision", C.c_float), ("collision_check", C.c_int32),
                 ("literal_no_collision", C.c_int32), ("max_iter", C.c_int32), ("tol_step", C.c_float),
-                ("reg_min", C.c_float), ("threads_per_block", C.c_int32), ("blocks_per_sm", C.c_int32)]
+                ("reg_min", C.c_float), ("threads_per_block", C.c_int32), ("blocks_per_sm", C.c_int32),
+                ("n_starts", C.c_int32)]
 
 
 class MpcProblemBatch(C.Structure):

@@ -49,13 +49,17 @@ class BatchedPureMPC:
     `weight_input_diff`).  The YAML's `weight_distance` / `weight_collision` are NOT read from cfg:
     the live agent's objective omits both terms (agents/pure_mpc.py:82, 204-212), so they are
     explicit constructor arguments defaulting to 0; pass `weight_distance=cfg["weight_distance"]`
-    for the archive objective (agents/archive/pure_mpc.py:189-226, BASELINE config 3)."""
+    for the archive objective (agents/archive/pure_mpc.py:189-226, BASELINE config 3).
+
+    n_starts: the NLP is multi-modal, so every problem is solved from `n_starts` starts (0 = the library default, 4)
+    and the lowest objective wins; start 0 is the reference's own cold start (zero controls,
+    agents/pure_mpc.py:244) and `n_starts=1` solves only that one (about 4x the throughput)."""
 
     def __init__(self, cfg: Dict, vehicles_count: int, max_batch: int, device: Union[int, str, torch.device] = 0,
                  dt: float = 0.1, collision_check: bool = True, literal_no_collision: bool = False,
                  weight_distance: float = 0.0, weight_collision: float = 0.0,
-                 max_iter: int = 60, tol_step: float = 1e-4, reg_min: float = 1e-2,
-                 threads_per_block: int = 0, blocks_per_sm: int = 0):
+                 max_iter: int = 100, tol_step: float = 1e-4, reg_min: float = 1e-2,
+                 threads_per_block: int = 0, blocks_per_sm: int = 0, n_starts: int = 0):
         if not torch.cuda.is_available():
             raise RuntimeError("BatchedPureMPC needs a CUDA device (B200, sm_100a); there is no CPU path")
         self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
@@ -68,6 +72,7 @@ class BatchedPureMPC:
         self.max_batch = int(max_batch)
         self.dt = float(dt)
         self.collision_check = bool(collision_check)
+        self.n_starts = int(n_starts) if int(n_starts) > 0 else 4
         c = _capi.MpcConfig(
             abi_version=_capi.ABI_VERSION, horizon=self.horizon, vehicles_count=self.vehicles_count, dt=self.dt,
             weight_speed=float(cfg.get("weight_speed", 1.0)), weight_control=float(cfg.get("weight_control", 1.0)),
@@ -75,7 +80,7 @@ class BatchedPureMPC:
             weight_distance=float(weight_distance), weight_collision=float(weight_collision),
             collision_check=int(collision_check), literal_no_collision=int(literal_no_collision),
             max_iter=int(max_iter), tol_step=float(tol_step), reg_min=float(reg_min),
-            threads_per_block=int(threads_per_block), blocks_per_sm=int(blocks_per_sm))
+            threads_per_block=int(threads_per_block), blocks_per_sm=int(blocks_per_sm), n_starts=int(n_starts))
         self._cfg = c
         h = C.c_void_p()
         idx = self.device.index if self.device.index is not None else torch.cuda.current_device()

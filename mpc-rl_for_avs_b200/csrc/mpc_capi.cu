@@ -31,6 +31,8 @@ struct MpcHandle {
   void* ws_block = nullptr;       // one allocation carved into the BatchWs arrays
   BatchWs ws{};
   int* work_counter = nullptr;
+  int n_starts = 1;
+  SolveCand cand{};                // candidate results of the start portfolio (n_starts > 1)
   const float* u_init = nullptr;   // opt-in warm start (device, borrowed)
   float* sink = nullptr;
   // host-call staging (mpc_predict_host)
@@ -73,6 +75,7 @@ MPC_API int mpc_destroy(MpcHandle* h) {
   for (auto e : h->ev_prepare) cudaEventDestroy(e);
   for (auto e : h->ev_solve) cudaEventDestroy(e);
   cudaFree(h->ws_block); cudaFree(h->work_counter); cudaFree(h->sink);
+  cudaFree(h->cand.cost); cudaFree(h->cand.u0); cudaFree(h->cand.status); cudaFree(h->cand.iters); cudaFree(h->cand.U);
   cudaFree(h->d_obs); cudaFree(h->d_ref_speed); cudaFree(h->d_weights); cudaFree(h->d_reset);
   cudaFree(h->d_actions); cudaFree(h->d_status); cudaFree(h->d_iters); cudaFree(h->d_cost);
   cudaFree(h->d_mem); cudaFree(h->d_memo); cudaFree(h->d_iscol);
@@ -92,6 +95,15 @@ MPC_API int mpc_create(const MpcConfig* cfg, int device, int max_batch, MpcHandl
     return fail(nullptr, MPC_ERR_BAD_ARG, "mpc_create: vehicles_count must be in 1..17");
   if (!(cfg->dt > 0.f)) return fail(nullptr, MPC_ERR_BAD_ARG, "mpc_create: dt must be positive");
   if (max_batch < 1) return fail(nullptr, MPC_ERR_BAD_ARG, "mpc_create: max_batch must be >= 1");
+  if (cfg->n_starts < 0 || cfg->n_starts > MPC_MAX_STARTS) return fail(nullptr, MPC_ERR_BAD_ARG, "mpc_create: n_starts must be in 0..8");
+  {   // dt enters the collision prediction as the double 1 / policy_frequency (agents/base_agent.py:43) and the dynamics
+      // as the float itself: both must be the same time step
+    const double f = 1.0 / (double)cfg->dt, fr = (double)(long long)(f + 0.5);
+    if (fr < 1.0 || (f - fr > 1e-4 * fr) || (fr - f > 1e-4 * fr))
+      return fail(nullptr, MPC_ERR_BAD_ARG, "mpc_create: dt must be 1 / (an integer policy frequency)");
+  }
+  const int n_starts = cfg->n_starts > 0 ? cfg->n_starts : 4;
+  if ((long long)max_batch * n_starts > 0x7fffffffLL / 64) return fail(nullptr, MPC_ERR_BAD_ARG, "mpc_create: max_batch * n_starts too large");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
     return fail(nullptr, MPC_ERR_NO_DEVICE, "mpc_create: no CUDA device (this library has no CPU path)");
@@ -105,6 +117,7 @@ MPC_API int mpc_create(const MpcConfig* cfg, int device, int max_batch, MpcHandl
   h->cfg = *cfg;
   h->device = device;
   h->max_batch = max_batch;
+  h->n_starts = n_starts;
   h->sm_count = prop.multiProcessorCount;
   h->cc_major = prop.major; h->cc_minor = prop.minor;
   h->smem_optin = (int)prop.sharedMemPerBlockOptin;
@@ -113,10 +126,11 @@ MPC_API int mpc_create(const MpcConfig* cfg, int device, int max_batch, MpcHandl
   s.N = N; s.M = M; s.dt = cfg->dt;
   s.w_distance = cfg->weight_distance; s.w_collision = cfg->weight_collision;
   s.literal_no_collision = cfg->literal_no_collision;
-  s.max_iter = cfg->max_iter > 0 ? cfg->max_iter : 60;
+  s.max_iter = cfg->max_iter > 0 ? cfg->max_iter : 100;
   s.tol_step = cfg->tol_step > 0.f ? cfg->tol_step : 1e-4f;
   s.reg_min = cfg->reg_min > 0.f ? cfg->reg_min : 1e-2f;
-  s.stall_tol = 1e-4f;
+  s.stall_tol = 0.f;
+  s.kink_tol = 1e-7f;
 
 #define CKC(call)                                                                        \
   do {                                                                                   \
@@ -127,12 +141,10 @@ MPC_API int mpc_create(const MpcConfig* cfg, int device, int max_batch, MpcHandl
   CKC(cudaSetDevice(device));
   // grid / block.  Default: gains in tensor memory, at most 256 problems (8 warps, two per scheduler) per SM --
   // up to 352 fit at H=20, M=8 and can be forced with threads_per_block, but measured no faster even at 1 M
-  // problems per launch; MPC_USE_TMEM=0 or a horizon whose gains do not fit the 512 TMEM columns selects
-  // the shared-memory kernel (192 problems / SM).
-  const char* env_tmem = getenv("MPC_USE_TMEM");
-  int want_tmem = env_tmem ? atoi(env_tmem) : 1;
+  // problems per launch; a horizon whose gains do not fit the 512 TMEM columns selects the shared-memory kernel
+  // (192 problems / SM).
   int tpb = 0;
-  if (want_tmem) {
+  {
     static const int cand[] = {384, 352, 320, 288, 256, 192, 128};
     const int cap = cfg->threads_per_block > 0 ? cfg->threads_per_block : 256;   // 256 is as fast as 352 at 1 M problems and faster below
     for (int c : cand) {
@@ -183,6 +195,14 @@ MPC_API int mpc_create(const MpcConfig* cfg, int device, int max_batch, MpcHandl
   h->ws.vr_slope = (float*)(base + o_vs); h->ws.vr_b = (float*)(base + o_vb); h->ws.vr_n = (int32_t*)(base + o_vn);
   h->ws.is_collide = (uint8_t*)(base + o_ic); h->ws.n_obs = (int32_t*)(base + o_no); h->ws.obstacles = (float*)(base + o_ob);
   CKC(cudaMalloc(&h->work_counter, sizeof(int)));
+  if (n_starts > 1) {
+    const size_t W = B * (size_t)n_starts;
+    CKC(cudaMalloc(&h->cand.cost, W * 4));
+    CKC(cudaMalloc(&h->cand.u0, W * 8));
+    CKC(cudaMalloc(&h->cand.status, W * 4));
+    CKC(cudaMalloc(&h->cand.iters, W * 4));
+    CKC(cudaMalloc(&h->cand.U, W * (size_t)N * 8));
+  }
   CKC(cudaMalloc(&h->sink, 256));
   // staging for the host-buffer entry point
   CKC(cudaMalloc(&h->d_obs, B * cfg->vehicles_count * 8 * 4));
@@ -268,23 +288,14 @@ static int timed_end(MpcHandle* h, std::vector<cudaEvent_t>& v, cudaStream_t st)
 // first (one block per SM), and only then grow the block.  Both kernels run the same per-problem code and
 // store the gains in the same packed form, so the result of a problem does not depend on the choice
 // (tests/test_gpu_parity.py::test_result_independent_of_batch_size).
-static void pick_solve_launch(const MpcHandle* h, int B, SolveLaunch& s) {
+static void pick_solve_launch(const MpcHandle* h, int B /* work items = problems x starts */, SolveLaunch& s) {
   s.threads_per_block = h->tpb; s.smem_bytes = h->smem; s.use_tmem = h->use_tmem;
   const int N = h->scfg.N, M = h->scfg.M;
   const int per_sm = (B + h->sm_count - 1) / h->sm_count;
   int want = (per_sm + 31) / 32 * 32;
-  static const int small_policy = getenv("MPC_SMALL_POLICY") ? atoi(getenv("MPC_SMALL_POLICY")) : 1;   // experiments: 0 = block ~ problems/SM
   if (!h->tpb_forced) {
     if (!h->use_tmem) {
       if (want < h->tpb) { s.threads_per_block = want; s.smem_bytes = solve_smem_bytes(N, M, want); }
-    } else if (small_policy == 0) {
-      if (want <= 96 && solve_smem_bytes(N, M, want) <= (size_t)h->smem_optin) {
-        s.use_tmem = 0; s.threads_per_block = want; s.smem_bytes = solve_smem_bytes(N, M, want);
-      } else {
-        int tpb = want <= 128 ? 128 : (want <= 192 ? 192 : 256);
-        if (tpb > h->tpb_small) tpb = h->tpb_small;
-        s.threads_per_block = tpb; s.smem_bytes = solve_smem_bytes_tmem(N, M, tpb);
-      }
     } else {
       // the 192/256-thread TMEM kernel at every size: a block that gets fewer problems than lanes packs them
       // into its lowest warps on the first trip and gives each 2-8 lanes to speculate with
@@ -295,14 +306,14 @@ static void pick_solve_launch(const MpcHandle* h, int B, SolveLaunch& s) {
   }
   // grid: one block per SM; small launches still spread over all SMs (>= 8 problems per block)
   int need = (B + s.threads_per_block - 1) / s.threads_per_block;
-  if (s.use_tmem && small_policy != 0) { const int spread = (B + 7) / 8; if (spread > need) need = spread; }
+  if (s.use_tmem) { const int spread = (B + 7) / 8; if (spread > need) need = spread; }
   s.grid = need < h->grid ? need : h->grid;
 }
 
 MPC_API int mpc_solve_config(const MpcHandle* h, int B, int* gains_in_tmem, int* threads_per_block) {
   if (!h || B < 0) return MPC_ERR_BAD_ARG;
   SolveLaunch s;
-  pick_solve_launch(h, B, s);
+  pick_solve_launch(h, B * h->n_starts, s);
   if (gains_in_tmem) *gains_in_tmem = s.use_tmem;
   if (threads_per_block) *threads_per_block = s.threads_per_block;
   return MPC_OK;
@@ -317,13 +328,16 @@ MPC_API int mpc_solve(MpcHandle* h, const MpcProblemBatch* batch, int B, const M
   CK(h, cudaSetDevice(h->device));
   CK(h, cudaMemsetAsync(h->work_counter, 0, sizeof(int), st));
   SolveLaunch s;
+  if (B > h->max_batch && h->n_starts > 1) return fail(h, MPC_ERR_TOO_LARGE, "mpc_solve: B exceeds max_batch of mpc_create");
   s.cfg = h->scfg; s.batch = *batch; s.out = *out; s.B = B; s.work_counter = h->work_counter;
+  s.n_starts = h->n_starts; s.cand = h->cand;
   s.u_init = h->u_init;
-  pick_solve_launch(h, B, s);
+  pick_solve_launch(h, B * h->n_starts, s);
   if ((rc = timed_begin(h, h->ev_solve, st))) return rc;
   CK(h, s.use_tmem ? launch_solve_tmem(s, st) : launch_solve(s, st));
-  if ((rc = timed_end(h, h->ev_solve, st))) return rc;
   h->launches += 1;
+  if (h->n_starts > 1) { CK(h, launch_select(s, st)); h->launches += 1; }
+  if ((rc = timed_end(h, h->ev_solve, st))) return rc;
   return MPC_OK;
 }
 

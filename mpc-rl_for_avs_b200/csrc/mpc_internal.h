@@ -45,13 +45,24 @@ cudaError_t launch_prepare(const PrepareParams& p, cudaStream_t stream);
 cudaError_t upload_ref_table_prepare();
 
 // defined in mpc_solve.cu
+// Candidate results of the start portfolio: work item w = start * B + problem.  Filled by the solve kernels when
+// n_starts > 1, reduced to MpcSolveOut by k_select (lowest objective wins, ties to the lowest start).
+struct SolveCand {
+  float* cost;            // [S * B]
+  float* u0;              // [S * B][2]
+  int32_t* status;        // [S * B]
+  int32_t* iters;         // [S * B]
+  float* U;               // [S * B][N][2]
+};
 struct SolveLaunch {
   SolverConfig cfg;
   MpcProblemBatch batch;
   MpcSolveOut out;
-  int B;
+  int B;                  // problems
+  int n_starts;           // work items = B * n_starts
+  SolveCand cand;         // used when n_starts > 1
   int* work_counter;      // device, zeroed before launch
-  const float* u_init;    // [B][N][2] warm start or null
+  const float* u_init;    // [B][N][2] warm start of start 0, or null
   int threads_per_block;
   int grid;
   size_t smem_bytes;
@@ -66,5 +77,6 @@ size_t solve_smem_bytes(int N, int M, int tpb);
 size_t solve_smem_bytes_tmem(int N, int M, int tpb);
 bool tmem_layout_fits(int N, int tpb);
 cudaError_t launch_solve_tmem(const SolveLaunch& s, cudaStream_t stream);
+cudaError_t launch_select(const SolveLaunch& s, cudaStream_t stream);
 
 }  // namespace mpcb

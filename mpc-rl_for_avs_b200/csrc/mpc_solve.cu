@@ -18,6 +18,8 @@
 //     lowest warps, and the freed lanes run the trips the sequential algorithm would run after 1, 2, ...
 //     rejections side by side (see the comments at kCompact / kSpec).
 //   * HBM traffic is the compulsory ~0.3 KB per problem: these kernels are FP32-issue / latency bound.
+#include <mutex>
+
 #include "mpc_internal.h"
 
 #include "ref_table.inc"
@@ -91,6 +93,56 @@ __device__ __forceinline__ void load_problem(const MpcProblemBatch& b, int B, in
   }
 }
 
+// work item -> (problem, start); first controls of a fresh item (cold start pure_mpc.py:244, a portfolio start, or the
+// opt-in warm start for start 0)
+template <typename SL>
+__device__ __forceinline__ void begin_item(const SolverConfig& cfg, const MpcProblemBatch& batch, int B, int idx, const float* __restrict__ u_init,
+                                           ProblemScalars<float>& p, const SL& sl, SolveState<float>& s) {
+  const int st = idx / B, pb = idx - st * B;
+  load_problem(batch, B, pb, cfg, p, sl);
+  solve_init(cfg, sl, s);
+  if (st > 0) {
+    apply_start<float>(cfg, sl, st);
+  } else if (u_init) {                  // opt-in warm start: the first rollout clamps it into the node boxes
+#pragma unroll 1
+    for (int k = 0; k < cfg.N; ++k) {
+      sl.U(k, 0) = u_init[((size_t)pb * cfg.N + k) * 2];
+      sl.U(k, 1) = u_init[((size_t)pb * cfg.N + k) * 2 + 1];
+    }
+  }
+}
+// result of a finished item: straight to the caller's arrays (one start) or to the candidate arrays (portfolio)
+template <typename SL>
+__device__ __forceinline__ void finish_item(const SolverConfig& cfg, const MpcSolveOut& out, const SolveCand& cand, int n_starts, int idx,
+                                            const SL& sl, SolveState<float>& s) {
+  if (!(s.J == s.J)) s.status |= kStatusNaN;
+  if (n_starts == 1) {
+    out.actions[2 * (size_t)idx] = sl.U(0, 0);
+    out.actions[2 * (size_t)idx + 1] = sl.U(0, 1);
+    if (out.status) out.status[idx] = s.status;
+    if (out.iters) out.iters[idx] = s.iter;
+    if (out.cost) out.cost[idx] = s.J;
+    if (out.U)
+#pragma unroll 1
+      for (int k = 0; k < cfg.N; ++k) {
+        out.U[((size_t)idx * cfg.N + k) * 2] = sl.U(k, 0);
+        out.U[((size_t)idx * cfg.N + k) * 2 + 1] = sl.U(k, 1);
+      }
+  } else {
+    cand.u0[2 * (size_t)idx] = sl.U(0, 0);
+    cand.u0[2 * (size_t)idx + 1] = sl.U(0, 1);
+    cand.status[idx] = s.status;
+    cand.iters[idx] = s.iter;
+    cand.cost[idx] = s.J;
+    if (out.U)
+#pragma unroll 1
+      for (int k = 0; k < cfg.N; ++k) {
+        cand.U[((size_t)idx * cfg.N + k) * 2] = sl.U(k, 0);
+        cand.U[((size_t)idx * cfg.N + k) * 2 + 1] = sl.U(k, 1);
+      }
+  }
+}
+
 // One trip of the loop = [fetch] -> backward sweep -> line-search passes -> commit sweep -> bookkeeping,
 // each with exactly ONE call site so the kernel body stays near the instruction-cache size (the
 // first profile showed 2.3 stall cycles per issued instruction waiting for instructions).
@@ -99,7 +151,7 @@ __device__ __forceinline__ void load_problem(const MpcProblemBatch& b, int B, in
 template <int TPB>
 __global__ void __launch_bounds__(TPB, 1)
 k_solve(const SolverConfig cfg, const MpcProblemBatch batch, const MpcSolveOut out, const int B, int* __restrict__ work_counter,
-        const float* __restrict__ u_init) {
+        const float* __restrict__ u_init, const int n_starts, const SolveCand cand) {
   extern __shared__ __align__(16) float smem[];
   const RefTab<float> ref = stage_tables(smem);
   using SL = Slots<float, true, TPB>;
@@ -115,17 +167,9 @@ k_solve(const SolverConfig cfg, const MpcProblemBatch batch, const MpcSolveOut o
     if (need_fetch) {
       need_fetch = false;
       idx = atomicAdd(work_counter, 1);
-      active = idx < B;
+      active = idx < B * n_starts;
       if (active) {
-        load_problem(batch, B, idx, cfg, p, sl);
-        solve_init(cfg, sl, s);
-        if (u_init) {                       // opt-in warm start: the first rollout clamps it into the node boxes
-#pragma unroll 1
-          for (int k = 0; k < cfg.N; ++k) {
-            sl.U(k, 0) = u_init[((size_t)idx * cfg.N + k) * 2];
-            sl.U(k, 1) = u_init[((size_t)idx * cfg.N + k) * 2 + 1];
-          }
-        }
+        begin_item(cfg, batch, B, idx, u_init, p, sl, s);
         fresh = true;
       }
     }
@@ -151,18 +195,7 @@ k_solve(const SolverConfig cfg, const MpcProblemBatch batch, const MpcSolveOut o
       } else {
         after_line_search(cfg, s, acc, alpha, Jn, md);
         if (s.done) {
-          if (!(s.J == s.J)) s.status |= kStatusNaN;
-          out.actions[2 * (size_t)idx] = sl.U(0, 0);
-          out.actions[2 * (size_t)idx + 1] = sl.U(0, 1);
-          if (out.status) out.status[idx] = s.status;
-          if (out.iters) out.iters[idx] = s.iter;
-          if (out.cost) out.cost[idx] = s.J;
-          if (out.U)
-#pragma unroll 1
-            for (int k = 0; k < cfg.N; ++k) {
-              out.U[((size_t)idx * cfg.N + k) * 2] = sl.U(k, 0);
-              out.U[((size_t)idx * cfg.N + k) * 2 + 1] = sl.U(k, 1);
-            }
+          finish_item(cfg, out, cand, n_starts, idx, sl, s);
           active = false;
           need_fetch = true;
         }
@@ -207,7 +240,7 @@ bool tmem_layout_fits(int N, int tpb) {
 template <int TPB>
 __global__ void __launch_bounds__(TPB, 1)
 k_solve_tmem(const SolverConfig cfg, const MpcProblemBatch batch, const MpcSolveOut out, const int B, int* __restrict__ work_counter,
-             const float* __restrict__ u_init) {
+             const float* __restrict__ u_init, const int n_starts, const SolveCand cand) {
   extern __shared__ __align__(16) float smem[];
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + kTabFloats);
   const int warp = threadIdx.x >> 5;
@@ -238,7 +271,7 @@ k_solve_tmem(const SolverConfig cfg, const MpcProblemBatch batch, const MpcSolve
   p.x0 = 0.0; p.y0 = 0.0; p.ego_index = 0; p.n_obs = 0; p.is_collide = 0;
   p.w_speed = 1.f; p.w_control = 1.f; p.w_diff = 1.f; p.vr_a = 0.f; p.vr_slope = 0.f; p.vr_b = 0.f; p.vr_n = 0;
   SolveState<float> s;
-  s.J = 0.f; s.mu = 0.f; s.hs = 1.f; s.J_mark = 0.f; s.iter = 0; s.status = 0; s.trials = 0; s.fails = 0; s.done = true;
+  s.J = 0.f; s.mu = 0.f; s.hs = 1.f; s.J_mark = 0.f; s.md_last = 1e30f; s.iter = 0; s.status = 0; s.trials = 0; s.fails = 0; s.done = true;
   int idx = -1;
   bool active = false, fresh = false, need_fetch = true, first_wave = true;
 
@@ -249,17 +282,9 @@ k_solve_tmem(const SolverConfig cfg, const MpcProblemBatch batch, const MpcSolve
       // atomics on one counter, and a small launch lands in the lowest lanes of every block; later: the shared queue
       idx = first_wave ? (int)(blockIdx.x + gridDim.x * threadIdx.x) : (int)(gridDim.x * TPB) + atomicAdd(work_counter, 1);
       first_wave = false;
-      active = idx < B;
+      active = idx < B * n_starts;
       if (active) {
-        load_problem(batch, B, idx, cfg, p, sl);
-        solve_init(cfg, sl, s);
-        if (u_init) {
-#pragma unroll 1
-          for (int k = 0; k < cfg.N; ++k) {
-            sl.U(k, 0) = u_init[((size_t)idx * cfg.N + k) * 2];
-            sl.U(k, 1) = u_init[((size_t)idx * cfg.N + k) * 2 + 1];
-          }
-        }
+        begin_item(cfg, batch, B, idx, u_init, p, sl, s);
         fresh = true;
       } else {
         saw_empty = true;
@@ -306,6 +331,7 @@ k_solve_tmem(const SolverConfig cfg, const MpcProblemBatch batch, const MpcSolve
           q[10] = __float_as_uint(p.vr_a); q[11] = __float_as_uint(p.vr_slope); q[12] = __float_as_uint(p.vr_b);
           q[13] = (uint32_t)p.vr_n;
           q[14] = __float_as_uint(s.J); q[15] = __float_as_uint(s.mu);    // s.hs is the constant 1 in every kernel: kept out of memory so it still folds
+          q[16] = __float_as_uint(s.md_last);
           q[17] = __float_as_uint(s.J_mark); q[18] = (uint32_t)s.iter; q[19] = (uint32_t)s.status;
           q[20] = (uint32_t)s.trials; q[21] = (uint32_t)s.fails;
           q[22] = (uint32_t)idx; q[23] = fresh ? 1u : 0u;
@@ -324,7 +350,7 @@ k_solve_tmem(const SolverConfig cfg, const MpcProblemBatch batch, const MpcSolve
           p.w_speed = __uint_as_float(q[7]); p.w_control = __uint_as_float(q[8]); p.w_diff = __uint_as_float(q[9]);
           p.vr_a = __uint_as_float(q[10]); p.vr_slope = __uint_as_float(q[11]); p.vr_b = __uint_as_float(q[12]);
           p.vr_n = (int)q[13];
-          s.J = __uint_as_float(q[14]); s.mu = __uint_as_float(q[15]);
+          s.J = __uint_as_float(q[14]); s.mu = __uint_as_float(q[15]); s.md_last = __uint_as_float(q[16]);
           s.J_mark = __uint_as_float(q[17]); s.iter = (int)q[18]; s.status = (int)q[19];
           s.trials = (int)q[20]; s.fails = (int)q[21]; s.done = false;
           idx = (int)q[22]; fresh = q[23] != 0u;
@@ -386,20 +412,7 @@ k_solve_tmem(const SolverConfig cfg, const MpcProblemBatch batch, const MpcSolve
         solve_init_finish(s, Jc);
         fresh = false;
       } else if (s.done) {
-        if (spec_j == 0) {
-          if (!(s.J == s.J)) s.status |= kStatusNaN;
-          out.actions[2 * (size_t)idx] = sl.U(0, 0);
-          out.actions[2 * (size_t)idx + 1] = sl.U(0, 1);
-          if (out.status) out.status[idx] = s.status;
-          if (out.iters) out.iters[idx] = s.iter;
-          if (out.cost) out.cost[idx] = s.J;
-          if (out.U)
-#pragma unroll 1
-            for (int k = 0; k < cfg.N; ++k) {
-              out.U[((size_t)idx * cfg.N + k) * 2] = sl.U(k, 0);
-              out.U[((size_t)idx * cfg.N + k) * 2 + 1] = sl.U(k, 1);
-            }
-        }
+        if (spec_j == 0) finish_item(cfg, out, cand, n_starts, idx, sl, s);
         active = false;
         spec_j = 0;
         need_fetch = !drained;                               // nothing left to fetch once a lane of the block saw the queue empty
@@ -411,14 +424,31 @@ k_solve_tmem(const SolverConfig cfg, const MpcProblemBatch batch, const MpcSolve
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" :: "r"(tmem_base) : "memory");
 }
 
-template <int TPB> static cudaError_t launch_solve_tmem_t(const SolveLaunch& s, cudaStream_t stream) {
-  static size_t configured = 0;
-  if (s.smem_bytes > configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_solve_tmem<TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.smem_bytes);
+// The opt-in dynamic shared memory size is a per-DEVICE function attribute: remember what was set per device (a
+// process may hold handles on several GPUs) and per kernel instantiation; guarded for concurrent host threads.
+constexpr int kMaxDevices = 64;
+struct SmemOptIn {
+  std::mutex m;
+  size_t configured[kMaxDevices] = {};
+  template <typename K> cudaError_t ensure(K kernel, size_t bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    configured = s.smem_bytes;
+    std::lock_guard<std::mutex> g(m);
+    if (dev < 0 || dev >= kMaxDevices || bytes > configured[dev]) {
+      e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+      if (e != cudaSuccess) return e;
+      if (dev >= 0 && dev < kMaxDevices) configured[dev] = bytes;
+    }
+    return cudaSuccess;
   }
-  k_solve_tmem<TPB><<<s.grid, TPB, s.smem_bytes, stream>>>(s.cfg, s.batch, s.out, s.B, s.work_counter, s.u_init);
+};
+
+template <int TPB> static cudaError_t launch_solve_tmem_t(const SolveLaunch& s, cudaStream_t stream) {
+  static SmemOptIn opt;
+  cudaError_t e = opt.ensure(k_solve_tmem<TPB>, s.smem_bytes);
+  if (e != cudaSuccess) return e;
+  k_solve_tmem<TPB><<<s.grid, TPB, s.smem_bytes, stream>>>(s.cfg, s.batch, s.out, s.B, s.work_counter, s.u_init, s.n_starts, s.cand);
   return cudaGetLastError();
 }
 
@@ -437,13 +467,10 @@ cudaError_t launch_solve_tmem(const SolveLaunch& s, cudaStream_t stream) {
 
 template <int TPB> static cudaError_t launch_solve_t(const SolveLaunch& s, cudaStream_t stream) {
   // handles with different horizon / obstacle counts share the kernel: raise the opt-in limit as needed
-  static size_t configured = 0;
-  if (s.smem_bytes > configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_solve<TPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.smem_bytes);
-    if (e != cudaSuccess) return e;
-    configured = s.smem_bytes;
-  }
-  k_solve<TPB><<<s.grid, TPB, s.smem_bytes, stream>>>(s.cfg, s.batch, s.out, s.B, s.work_counter, s.u_init);
+  static SmemOptIn opt;
+  cudaError_t e = opt.ensure(k_solve<TPB>, s.smem_bytes);
+  if (e != cudaSuccess) return e;
+  k_solve<TPB><<<s.grid, TPB, s.smem_bytes, stream>>>(s.cfg, s.batch, s.out, s.B, s.work_counter, s.u_init, s.n_starts, s.cand);
   return cudaGetLastError();
 }
 
@@ -457,6 +484,34 @@ cudaError_t launch_solve(const SolveLaunch& s, cudaStream_t stream) {
     case 192: return launch_solve_t<192>(s, stream);
     default: return cudaErrorInvalidConfiguration;
   }
+}
+
+// ---- start portfolio: per problem, the candidate with the lowest objective wins (ties: lowest start) --------------
+__global__ void __launch_bounds__(256)
+k_select(const int B, const int S, const int N, const SolveCand cand, const MpcSolveOut out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  int best = 0, it = 0;
+  float Jb = 0.f;
+  for (int st = 0; st < S; ++st) {
+    const float J = cand.cost[(size_t)st * B + b];
+    it += cand.iters[(size_t)st * B + b];
+    if (st == 0 || J < Jb) { Jb = J; best = st; }       // NaN never wins over a finite start 0; a NaN start 0 is replaced by any finite one
+    if (st > 0 && !(Jb == Jb) && J == J) { Jb = J; best = st; }
+  }
+  const size_t w = (size_t)best * B + b;
+  out.actions[2 * (size_t)b] = cand.u0[2 * w];
+  out.actions[2 * (size_t)b + 1] = cand.u0[2 * w + 1];
+  if (out.status) out.status[b] = cand.status[w];
+  if (out.iters) out.iters[b] = it;                     // total over the starts: the work this problem cost
+  if (out.cost) out.cost[b] = Jb;
+  if (out.U)
+    for (int k = 0; k < 2 * N; ++k) out.U[(size_t)b * 2 * N + k] = cand.U[w * 2 * N + k];
+}
+
+cudaError_t launch_select(const SolveLaunch& s, cudaStream_t stream) {
+  k_select<<<(s.B + 255) / 256, 256, 0, stream>>>(s.B, s.n_starts, s.cfg.N, s.cand, s.out);
+  return cudaGetLastError();
 }
 
 // ---- K1 parity entry: rollout + six cost components for given controls -----------------------

@@ -555,16 +555,22 @@ def _orient(ax, ay, bx, by, cx, cy):
 def polyline_intersections(E: np.ndarray, O: np.ndarray, degenerate_eps: float = 1e-9):
     """Intersection candidates of two polylines, standing in for
     `LineString(E).intersection(LineString(O))` + the geometry-type dispatch of
-    agents/pure_mpc.py:608-633.
+    agents/pure_mpc.py:608-633.  E = the ego's polyline, O = the other vehicle's straight 31-point track.
 
-    Proper crossings and endpoint touches of segment pairs yield points (deduplicated);
-    candidates are returned in lexicographic (x, then y) order -- the order GEOS' overlay
-    emits the members of a MultiPoint, as far as it can be established without GEOS
-    (ASSUMPTION).  Collinear overlaps (GEOS: (Multi)LineString) contribute
-    the far end of the overlap (coords[len//2] of a 2-point LineString).  Returns
-    (points (K,2), degenerate flag): the flag is set when any tested orientation is within
-    `degenerate_eps` (relative) of zero without being a clean miss, i.e. when robust and
-    plain predicates could disagree."""
+    * Proper crossings and exact endpoint touches of segment pairs yield points (deduplicated), returned in
+      lexicographic (x, then y) order -- the order GEOS' overlay emits the members of a MultiPoint, as far as it can be
+      established without GEOS (ASSUMPTION).
+    * Collinear overlaps (an ego segment and the track on the same line, all four orientations exactly zero -- the
+      same-lane case: highway-env's lane centre x = 2.0 is the reference path's own x) make GEOS return a
+      LineString per connected overlap whose coordinates are the merged vertices of both inputs inside the overlap;
+      the reference takes `coords[len(coords) // 2]` (pure_mpc.py:618-622, :628-633).  Vertex order: along the ego
+      polyline, the first operand of `ego_path.intersection(agent_path)` (ASSUMPTION; it only matters for an even
+      number of vertices).  Isolated points that lie on an overlap belong to it.
+    * A result that mixes overlaps with isolated points is a GeometryCollection, which the reference's dispatch does
+      not handle: no candidate at all (pure_mpc.py:615-633 has no branch for it).
+    Returns (points (K,2), degenerate flag): the flag is set when a tested orientation is within
+    `degenerate_eps` (relative) of zero WITHOUT being exactly zero, i.e. when GEOS' robust predicates and
+    plain FP64 could disagree."""
     ne, no = E.shape[0] - 1, O.shape[0] - 1
     if ne < 1 or no < 1:
         return np.zeros((0, 2)), False
@@ -582,33 +588,66 @@ def polyline_intersections(E: np.ndarray, O: np.ndarray, degenerate_eps: float =
     for i, j in zip(ii, jj):
         t = d1[i, j] / (d1[i, j] - d2[i, j])
         pts.append((E[i, 0] + t * (E[i + 1, 0] - E[i, 0]), E[i, 1] + t * (E[i + 1, 1] - E[i, 1])))
-    # near-degenerate bookkeeping: a pair whose bounding boxes overlap and that has a
-    # (near-)zero orientation among its four
-    near = ((np.abs(d1) <= degenerate_eps * scale) | (np.abs(d2) <= degenerate_eps * scale)
-            | (np.abs(d3) <= degenerate_eps * scale) | (np.abs(d4) <= degenerate_eps * scale))
     bb = ((np.minimum(p1[..., 0], p2[..., 0]) <= np.maximum(q1[..., 0], q2[..., 0]) + 1e-9)
           & (np.minimum(q1[..., 0], q2[..., 0]) <= np.maximum(p1[..., 0], p2[..., 0]) + 1e-9)
           & (np.minimum(p1[..., 1], p2[..., 1]) <= np.maximum(q1[..., 1], q2[..., 1]) + 1e-9)
           & (np.minimum(q1[..., 1], q2[..., 1]) <= np.maximum(p1[..., 1], p2[..., 1]) + 1e-9))
+    near = ((np.abs(d1) <= degenerate_eps * scale) | (np.abs(d2) <= degenerate_eps * scale)
+            | (np.abs(d3) <= degenerate_eps * scale) | (np.abs(d4) <= degenerate_eps * scale))
+    allzero = (d1 == 0) & (d2 == 0) & (d3 == 0) & (d4 == 0)
+    # ---- collinear overlaps: the track is one straight line, so "ego segment i lies on it" does not depend on j
+    O0, O1 = O[0], O[-1]
+    dO = O1 - O0
+    ax = 0 if abs(dO[0]) >= abs(dO[1]) else 1          # scalar coordinate along the line: the dominant axis
+    olo, ohi = min(O0[ax], O1[ax]), max(O0[ax], O1[ax])
+    pieces = []                                         # [lo, hi] along `ax`, in ego order, touching pieces merged
+    on_line = np.zeros(ne, bool)
+    if ohi > olo:
+        for i in range(ne):
+            if not np.all(allzero[i]):
+                continue
+            a, b = E[i][ax], E[i + 1][ax]
+            if a == b:
+                continue
+            on_line[i] = True
+            lo, hi = max(min(a, b), olo), min(max(a, b), ohi)
+            if hi > lo:
+                if pieces and (pieces[-1][0] == hi or pieces[-1][1] == lo):
+                    pieces[-1] = [min(pieces[-1][0], lo), max(pieces[-1][1], hi), pieces[-1][2]]
+                else:
+                    pieces.append([lo, hi, 1 if b > a else -1])
+    # ---- touches (exactly zero orientation with the touching endpoint on the other segment) and near-degenerate pairs
     touch = near & bb & ~proper
     if np.any(touch):
         ti, tj = np.nonzero(touch)
         for i, j in zip(ti, tj):
+            if on_line[i]:
+                continue                                 # handled as an overlap
             a, b, c, d = E[i], E[i + 1], O[j], O[j + 1]
             o = (d1[i, j], d2[i, j], d3[i, j], d4[i, j])
 
             def on_seg(p, s, e):
-                return (min(s[0], e[0]) - 1e-12 <= p[0] <= max(s[0], e[0]) + 1e-12
-                        and min(s[1], e[1]) - 1e-12 <= p[1] <= max(s[1], e[1]) + 1e-12)
+                return (min(s[0], e[0]) <= p[0] <= max(s[0], e[0]) and min(s[1], e[1]) <= p[1] <= max(s[1], e[1]))
             exact = [o[0] == 0 and on_seg(a, c, d), o[1] == 0 and on_seg(b, c, d),
                      o[2] == 0 and on_seg(c, a, b), o[3] == 0 and on_seg(d, a, b)]
-            # exact touches are genuine intersection points; collinear overlaps give several
             for flag, p in zip(exact, (a, b, c, d)):
                 if flag:
                     pts.append((float(p[0]), float(p[1])))
-            # exact touch where the other pair of orientations still separates is benign,
-            # everything else near zero is flagged
-            degenerate = True
+            if any(v != 0 and abs(v) <= degenerate_eps * scale[i, j] for v in o):
+                degenerate = True                        # near zero but not zero: robust and plain predicates may differ
+    if pieces:
+        # isolated points that are not part of an overlap -> GeometryCollection -> the reference finds nothing
+        def in_piece(p):
+            return any(lo <= p[ax] <= hi for lo, hi, _ in pieces) and _orient(O0[0], O0[1], O1[0], O1[1], p[0], p[1]) == 0
+        if any(not in_piece(p) for p in pts):
+            return np.zeros((0, 2)), degenerate
+        mids = []
+        for lo, hi, sgn in pieces:
+            vs = [tuple(v) for v in E if lo <= v[ax] <= hi and _orient(O0[0], O0[1], O1[0], O1[1], v[0], v[1]) == 0]
+            vs += [tuple(v) for v in O if lo <= v[ax] <= hi]
+            vs = sorted(set(vs), key=lambda v: sgn * v[ax])
+            mids.append(vs[len(vs) // 2])
+        return np.array(mids, dtype=np.float64), degenerate
     if not pts:
         return np.zeros((0, 2)), degenerate
     arr = np.unique(np.array(pts), axis=0)      # lexicographic (x, y) + exact dedup

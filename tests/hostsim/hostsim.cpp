@@ -72,24 +72,35 @@ static void make_ref(const double* ref85x4, HostTables<T>& out) {
 
 template <typename T, bool kPack>
 static void run_solve(const SolverConfig& cfg, const double* ref, const HsBatch& b, int B, float* actions,
-                      int* status, int* iters, float* cost, float* U_out, int* outer_out) {
+                      int* status, int* iters, float* cost, float* U_out, int* outer_out, const float* u_init = nullptr,
+                      int n_starts = 1) {
   HostTables<T> rt;
   make_ref(ref, rt);
   std::vector<T> buf(slots_per_problem(cfg.N, cfg.M, kPack));
   for (int i = 0; i < B; ++i) {
-    Slots<T, kPack> sl{buf.data(), 1, cfg.N, cfg.M};
-    ProblemScalars<T> p;
-    load_problem(b, B, i, cfg, p, sl);
-    SolveState<T> s;
-    solve_one(cfg, p, rt.tab(), sl, s);
-    actions[2 * i] = float(sl.U(0, 0));
-    actions[2 * i + 1] = float(sl.U(0, 1));
-    status[i] = s.status;
-    iters[i] = s.iter;
-    if (outer_out) outer_out[i] = s.fails;
-    cost[i] = float(s.J);
-    if (U_out)
-      for (int k = 0; k < cfg.N; ++k) { U_out[((size_t)i * cfg.N + k) * 2] = float(sl.U(k, 0)); U_out[((size_t)i * cfg.N + k) * 2 + 1] = float(sl.U(k, 1)); }
+    // start portfolio as in the product (k_solve + k_select): every start is an independent solve, the lowest
+    // FP objective wins (ties: lowest start), `iters` is the total over the starts
+    float best = 0.f;
+    int it_total = 0;
+    for (int st = 0; st < n_starts; ++st) {
+      Slots<T, kPack> sl{buf.data(), 1, cfg.N, cfg.M};
+      ProblemScalars<T> p;
+      load_problem(b, B, i, cfg, p, sl);
+      SolveState<T> s;
+      solve_one(cfg, p, rt.tab(), sl, s, u_init ? u_init + (size_t)i * cfg.N * 2 : nullptr, st);
+      it_total += s.iter;
+      const float J = float(s.J);
+      if (st > 0 && !(J < best) && !(!(best == best) && J == J)) continue;
+      best = J;
+      actions[2 * i] = float(sl.U(0, 0));
+      actions[2 * i + 1] = float(sl.U(0, 1));
+      status[i] = s.status;
+      if (outer_out) outer_out[i] = s.fails;
+      cost[i] = J;
+      if (U_out)
+        for (int k = 0; k < cfg.N; ++k) { U_out[((size_t)i * cfg.N + k) * 2] = float(sl.U(k, 0)); U_out[((size_t)i * cfg.N + k) * 2 + 1] = float(sl.U(k, 1)); }
+    }
+    iters[i] = it_total;
   }
 }
 
@@ -130,6 +141,14 @@ int hs_solve(const SolverConfig* cfg, const double* ref85x4, const HsBatch* b, i
   if (use_double == 1) run_solve<double, false>(*cfg, ref85x4, *b, B, actions, status, iters, cost, U_out, outer_out);
   else if (use_double == 2) run_solve<float, false>(*cfg, ref85x4, *b, B, actions, status, iters, cost, U_out, outer_out);
   else run_solve<float, true>(*cfg, ref85x4, *b, B, actions, status, iters, cost, U_out, outer_out);
+  return 0;
+}
+
+// opt-in warm start (the product's mpc_set_warm_start): u_init [B][N][2]
+int hs_solve_init(const SolverConfig* cfg, const double* ref85x4, const HsBatch* b, int B, int use_double, const float* u_init,
+                  int n_starts, float* actions, int* status, int* iters, float* cost, float* U_out) {
+  if (use_double == 1) run_solve<double, false>(*cfg, ref85x4, *b, B, actions, status, iters, cost, U_out, nullptr, u_init, n_starts);
+  else run_solve<float, true>(*cfg, ref85x4, *b, B, actions, status, iters, cost, U_out, nullptr, u_init, n_starts);
   return 0;
 }
 

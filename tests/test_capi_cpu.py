@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_the_header():
     capi = _capi()
-    assert C.sizeof(capi.MpcConfig) == 16 * 4
+    assert C.sizeof(capi.MpcConfig) == 17 * 4
     assert C.sizeof(capi.MpcProblemBatch) == 12 * C.sizeof(C.c_void_p)
     assert C.sizeof(capi.MpcSolveOut) == 5 * C.sizeof(C.c_void_p)
     assert C.sizeof(capi.MpcLatchState) == 3 * C.sizeof(C.c_void_p)
@@ -41,7 +41,7 @@ def test_create_rejects_bad_arguments_and_missing_device():
     h = C.c_void_p()
     good = dict(abi_version=capi.ABI_VERSION, horizon=20, vehicles_count=9, dt=0.1, weight_speed=1, weight_control=1,
                 weight_input_diff=1)
-    for bad in (dict(abi_version=99), dict(horizon=1), dict(horizon=65), dict(vehicles_count=0), dict(vehicles_count=18), dict(dt=0.0)):
+    for bad in (dict(abi_version=99), dict(horizon=1), dict(horizon=65), dict(vehicles_count=0), dict(vehicles_count=18), dict(dt=0.0), dict(dt=0.15), dict(n_starts=9), dict(n_starts=-1)):
         cfg = capi.MpcConfig(**{**good, **bad})
         assert lib.mpc_create(C.byref(cfg), 0, 16, C.byref(h)) == capi.ERR_BAD_ARG
         assert lib.mpc_last_error(None)

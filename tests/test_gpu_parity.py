@@ -141,71 +141,79 @@ def test_latch_sequence_matches_oracle_agent():
 
 
 # --------------------------------------------------------------------------------------- K2
-def _solve_and_compare(g, M, wd):
+_SOLVE_CACHE = {}
+
+
+def _solve_golden(name, M, wd, n_starts):
+    """CUDA solve of a golden set from the reference's cold start (n_starts = 1) or with the default start portfolio."""
+    key = (name, n_starts)
+    if key in _SOLVE_CACHE:
+        return _SOLVE_CACHE[key]
+    g = helpers.load_golden(name)
     probs = _problems_from_golden(g)
     B = len(probs)
-    agent = _pkg().BatchedPureMPC(CFG, vehicles_count=M + 1, max_batch=B, collision_check=False, weight_distance=wd)
+    agent = _pkg().BatchedPureMPC(CFG, vehicles_count=M + 1, max_batch=B, collision_check=False, weight_distance=wd, n_starts=n_starts)
     actions, U = agent.solve_batch(_to_dev(_golden_batch(g)), return_controls=True)
     torch.cuda.synchronize()
-    actions, U = actions.cpu().numpy(), U.cpu().numpy()
-    status = agent.status[:B].cpu().numpy()
-    iters = agent.iters[:B].cpu().numpy()
-    cost64 = np.array([orc.objective(U[i].astype(np.float64), probs[i]) for i in range(B)])
-    du = np.max(np.abs(actions - g["oracle_U"][:, 0, :]), axis=1)
-    same = du <= 1e-3
-    below = cost64 <= g["oracle_cost"] * (1 + 1e-6) + 1e-6
-    return dict(probs=probs, actions=actions, U=U, status=status, iters=iters, cost64=cost64, same=same, below=below,
-                cost32=agent.cost[:B].cpu().numpy())
+    r = dict(actions=actions.cpu().numpy(), U=U.cpu().numpy(), status=agent.status[:B].cpu().numpy(),
+             iters=agent.iters[:B].cpu().numpy(), cost=agent.cost[:B].cpu().numpy())
+    _SOLVE_CACHE[key] = (g, probs, r)
+    return _SOLVE_CACHE[key]
 
 
-@pytest.mark.parametrize("name,M,wd,min_same,min_below", [("golden_track", 0, 0.0, 0.80, 0.85),
-                                                          ("golden_coll", 8, 10.0, 0.60, 0.85)])
-def test_solve_against_golden_cold_start(name, M, wd, min_same, min_below):
-    """Cold-start agreement with the oracle's optimum.  The NLP is multi-modal (the steering weight is
-    0.01 and the Euler slip model admits zig-zag minima), so two local solvers started at U = 0 do not
-    always land in the same basin; where they do the first control agrees to 1e-3 and the GPU cost is
-    at or below the oracle's."""
-    g = helpers.load_golden(name)
-    r = _solve_and_compare(g, M, wd)
-    conv = r["status"] == 0
-    assert conv.mean() >= 0.88, conv.mean()
-    assert r["same"].mean() >= min_same, r["same"].mean()
-    assert r["below"].mean() >= min_below, r["below"].mean()
+@pytest.mark.parametrize("name,M,wd", [("golden_track", 0, 0.0), ("golden_coll", 8, 10.0)])
+@pytest.mark.parametrize("n_starts", [4, 1])
+def test_solve_against_best_known_optimum(name, M, wd, n_starts):
+    """The solve against the yardstick of oracle/ipm_oracle.py: the best CONFIRMED local optimum found by the
+    IPOPT-like interior point on the reference's literal multiple-shooting NLP (from its own cold start) and by SLSQP
+    on the single-shooting form.  The NLP is multi-modal (steering costs 0.01, the Euler slip model admits zig-zag
+    minima, 1/d^2 obstacle potentials), so agreement is a rate; helpers.PARITY_BARS holds the bars, overall and for the
+    problems whose horizon stays on the reference path."""
+    g, probs, r = _solve_golden(name, M, wd, n_starts)
+    st = helpers.solve_parity_stats(r, g, probs)
+    for tag in ("all", "in_path"):
+        print(f"{name} n_starts {n_starts} {tag}: " + " ".join(f"{k} {v:.3f}" for k, v in st[tag].items() if k != "n"))
+    helpers.assert_parity_bars(st, name, n_starts)
     # same first control almost always means the same optimum (a shared pinned first control with a
     # different tail is the exception): then the costs agree
-    rel = np.abs(r["cost64"] - g["oracle_cost"]) / np.maximum(np.abs(g["oracle_cost"]), 1.0)
-    assert np.mean(rel[r["same"] & conv] <= 1e-4) >= 0.9
+    rel = np.abs(st["cost64"] - g["oracle_cost"]) / np.maximum(np.abs(g["oracle_cost"]), 1.0)
+    assert np.mean(rel[st["same_mask"] & st["conv_mask"]] <= 1e-4) >= 0.9
     # reported FP32 cost is the objective of the returned controls (away from the d = 1 jump)
-    for i in range(len(r["probs"])):
-        near_disc, dist_tol = helpers.distance_conditioning(r["probs"][i], r["U"][i])
+    for i in range(len(probs)):
+        near_disc, dist_tol = helpers.distance_conditioning(probs[i], r["U"][i])
         if not near_disc:
-            assert abs(r["cost32"][i] - r["cost64"][i]) <= 2e-5 * max(abs(r["cost64"][i]), 1.0) + wd * dist_tol, i
-    print(f"{name}: converged {conv.mean():.3f} same-u0 {r['same'].mean():.3f} cost<=oracle {r['below'].mean():.3f} "
-          f"iters mean {r['iters'].mean():.1f} p50 {np.median(r['iters'])} p99 {np.percentile(r['iters'], 99)}")
+            assert abs(r["cost"][i] - st["cost64"][i]) <= 2e-5 * max(abs(st["cost64"][i]), 1.0) + wd * dist_tol, i
+    # the total iteration count covers every start
+    assert r["iters"].min() >= n_starts
 
 
 @pytest.mark.parametrize("name,M,wd", [("golden_track", 0, 0.0), ("golden_coll", 8, 10.0)])
 def test_every_converged_solution_is_confirmed_by_the_oracle(name, M, wd):
     """Started at the GPU's controls, the oracle's NLP solver must stay there: first control within
     1e-3 and no cost reduction beyond 1e-6 relative.  This is the optimality statement that does not
-    depend on which basin a cold start falls into; it must hold for EVERY converged problem."""
-    g = helpers.load_golden(name)
-    r = _solve_and_compare(g, M, wd)
-    idx = np.nonzero(r["status"] == 0)[0][:96]
+    depend on which basin a cold start falls into; it must hold for EVERY problem returned with status 0.
+    (Problems that settle on a kink of the clamped dynamics carry MPC_STATUS_KINK instead: most are optima too, the
+    rate is printed.)"""
+    g, probs, r = _solve_golden(name, M, wd, 4)
+    idx = np.nonzero(r["status"] == 0)[0]
     bad = []
     for i in idx:
-        ok, du0, gain = helpers.oracle_warm_confirms(r["probs"][i], r["U"][i])
+        ok, du0, gain = helpers.oracle_warm_confirms(probs[i], r["U"][i])
         if not ok:
             bad.append((int(i), du0, gain))
     assert not bad, bad
+    kink = np.nonzero(r["status"] == 32)[0]
+    n_ok = sum(helpers.oracle_warm_confirms(probs[i], r["U"][i])[0] for i in kink)
+    print(f"{name}: status 0 {len(idx)} all confirmed; kink {len(kink)}, {n_ok} of them confirmed")
     # solver-independent certificate: first-order (KKT) residual of the reference NLP at the GPU controls,
     # multipliers by non-negative least squares over the constraints within 1e-4 of active
-    kkt = np.array([orc.kkt_residual(r["U"][i].astype(np.float64), r["probs"][i], 1e-4)[0] for i in idx])
-    scale = 1.0 + np.abs(r["cost64"][idx])
+    cost64 = np.array([orc.objective(r["U"][i].astype(np.float64), probs[i]) for i in idx])
+    kkt = np.array([orc.kkt_residual(r["U"][i].astype(np.float64), probs[i], 1e-4)[0] for i in idx])
+    scale = 1.0 + np.abs(cost64)
     assert np.median(kkt / scale) <= 1e-5 and np.mean(kkt / scale <= 1e-3) >= 0.97, (np.median(kkt / scale), np.max(kkt / scale))
     # bounds of the reference NLP hold on every returned iterate, converged or not
-    for i in range(len(r["probs"])):
-        X = orc.rollout(r["probs"][i].s0, r["U"][i].astype(np.float64))
+    for i in range(len(probs)):
+        X = orc.rollout(probs[i].s0, r["U"][i].astype(np.float64))
         assert np.all(np.abs(r["U"][i][:, 0]) <= 5 + 1e-6) and np.all(np.abs(r["U"][i][:, 1]) <= np.pi / 3 + 1e-6)
         assert X[1:, 3].min() >= -1e-4 and X[1:, 3].max() <= 30 + 1e-4
         assert np.abs(X[1:, 2]).max() <= np.pi + 1e-4
@@ -223,7 +231,7 @@ def test_survey_known_answers():
         s0 = np.array(s0, float)
         idx = orc.nearest_index(s0[:2], ref[:, :2])
         probs.append(orc.Problem(s0=s0, ego_index=idx, ref_v=ref[np.minimum(idx + np.arange(20), 84), 2].copy()))
-    agent = _pkg().BatchedPureMPC(CFG, vehicles_count=1, max_batch=len(probs), collision_check=False)
+    agent = _pkg().BatchedPureMPC(CFG, vehicles_count=1, max_batch=len(probs), collision_check=False, n_starts=1)
     actions = agent.solve_batch(_to_dev(helpers.batch_from_problems(probs, 0))).cpu().numpy()
     cost = agent.cost[: len(probs)].cpu().numpy()
     for i, (_, f, u0) in enumerate(cases):
@@ -311,7 +319,7 @@ def test_full_size_properties():
     assert torch.isfinite(a).all()
     assert (a[:, 0].abs() <= 5 + 1e-6).all() and (a[:, 1].abs() <= np.pi / 3 + 1e-6).all()
     assert ((st & 4) == 0).all()
-    assert (st == 0).float().mean() >= 0.85
+    assert ((st & ~32) == 0).float().mean() >= 0.93 and (st == 0).float().mean() >= 0.85
     # a permuted sub-batch gives bit-identical actions for the same environments
     perm = torch.randperm(4096, generator=torch.Generator().manual_seed(0))
     agent2 = pkg.BatchedPureMPC(CFG, vehicles_count=M + 1, max_batch=4096, collision_check=True, weight_distance=10.0)
@@ -448,7 +456,7 @@ def test_shipped_config_horizon16_ten_vehicles():
     assert np.array_equal(agent.is_collide[:B].cpu().numpy().astype(bool)[nd], np.array([p.is_collide for p in probs])[nd])
     assert np.array_equal(agent.ego_index[:B].cpu().numpy(), np.array([p.ego_index for p in probs]))
     st = agent.status[:B].cpu().numpy()
-    assert (st == 0).mean() >= 0.8
+    assert ((st & ~32) == 0).mean() >= 0.9 and (st == 0).mean() >= 0.75
     for i in np.nonzero((st == 0) & nd)[0][:24]:
         ok, du0, gain = helpers.oracle_warm_confirms(probs[i], U[i])
         assert ok, (i, du0, gain)
@@ -467,7 +475,7 @@ def test_long_horizons_fall_back_to_the_kernels_that_fit(N, expect_tmem, expect_
     B, M = 600, 8
     cfg = dict(CFG, horizon=N)
     obs, rs, has = pkg.make_scenarios(B, M, seed=17)
-    agent = pkg.BatchedPureMPC(cfg, vehicles_count=M + 1, max_batch=B, collision_check=True, weight_distance=10.0, max_iter=80)
+    agent = pkg.BatchedPureMPC(cfg, vehicles_count=M + 1, max_batch=B, collision_check=True, weight_distance=10.0, max_iter=80, n_starts=1)
     sc = agent.solve_config(B)
     assert sc["gains_in_tmem"] == expect_tmem and (expect_tpb is None or sc["threads_per_block"] == expect_tpb), sc
     actions, U = agent.predict_batch(obs.cuda(), return_controls=True)
@@ -524,7 +532,7 @@ def test_config2_4096_no_collision_batch():
     a, U = agent.predict_batch(obs.cuda(), ref_speed=rsn, return_controls=True)
     torch.cuda.synchronize()
     st = agent.status[:B].cpu().numpy()
-    assert (st == 0).mean() >= 0.85 and torch.isfinite(a).all()
+    assert ((st & ~32) == 0).mean() >= 0.95 and (st == 0).mean() >= 0.85 and torch.isfinite(a).all()
     probs, _ = helpers.problems_from_obs(obs.numpy()[:64], rs.numpy()[:64], has.numpy()[:64])
     U = U.cpu().numpy()
     for i in np.nonzero(st[:64] == 0)[0][:24]:
@@ -539,7 +547,7 @@ def test_opt_in_warm_start():
     pkg = _pkg()
     B, M = 256, 8
     obs, _, _ = pkg.make_scenarios(B, M, seed=61, v_max=9.5)
-    agent = pkg.BatchedPureMPC(CFG, vehicles_count=M + 1, max_batch=B, collision_check=False, weight_distance=10.0)
+    agent = pkg.BatchedPureMPC(CFG, vehicles_count=M + 1, max_batch=B, collision_check=False, weight_distance=10.0, n_starts=1)
     a0, U0 = agent.predict_batch(obs.cuda(), return_controls=True)
     a0, it0, st0 = a0.clone(), agent.iters[:B].clone(), agent.status[:B].clone()
     # advance the ego along its first optimal control and the others at constant velocity (one policy step)

@@ -152,9 +152,49 @@ def test_oracle_reproduces_golden_fixtures():
         d = helpers.batch_from_problems(probs, int(g["n_obstacles"]))
         for k, v in d.items():
             assert np.array_equal(v, g["batch_" + k][..., :24] if v.ndim > 1 else g["batch_" + k][:24]), k
-        for i in range(0, 24, 4):
-            s = orc.solve_nlp(probs[i])
-            assert abs(s.cost - g["oracle_cost"][i]) <= 1e-7 * max(1.0, abs(s.cost))
-            assert np.allclose(s.U, g["oracle_U"][i], atol=1e-6)
+        import ipm_oracle as ipm
+        for i in (0, 12):
+            b = ipm.best_known_optimum(probs[i])
+            assert abs(b["cost"] - g["oracle_cost"][i]) <= 1e-9 * max(1.0, abs(b["cost"]))
+            assert np.allclose(b["U"], g["oracle_U"][i], atol=1e-9) and b["source"] == str(g["oracle_source"][i])
+            assert np.allclose(b["ipm_raw_U"], g["ipm_raw_U"][i], atol=1e-9) and b["ipm_status"] == str(g["ipm_status"][i])
             c = orc.cost_components(orc.rollout(probs[i].s0, g["oracle_U"][i]), g["oracle_U"][i], probs[i])
             assert np.allclose(c, g["oracle_components"][i], rtol=1e-9, atol=1e-9)
+
+
+def test_ipm_oracle_derivatives_and_known_answers():
+    """The IPOPT-like interior point on the literal multiple-shooting NLP (oracle/ipm_oracle.py): analytic gradient,
+    Jacobian and Lagrangian Hessian against central differences, and the survey's independently derived optima
+     from the reference's own cold start z0 = [tile(s0), 0]."""
+    import ipm_oracle as ipm
+    ref = helpers.REF
+    rng = np.random.default_rng(0)
+    s0 = np.array([3, 30, -np.pi / 2 + 0.1, 5.0])
+    idx = orc.nearest_index(s0[:2], ref[:, :2])
+    others = np.array([[5., 25., 8., np.pi], [0., 20., 7., 0.3]])
+    p = orc.Problem(s0=s0, ego_index=idx, ref_v=ref[np.minimum(idx + np.arange(20), 84), 2].copy(), w_distance=10.0, others=others)
+    nlp = ipm.LiteralNLP(p)
+    assert nlp.n == 124 and nlp.m == 84                                   # agents/pure_mpc.py:260, :249-257
+    z = nlp.z0 + rng.normal(0, 0.3, nlp.n)
+    g, _ = nlp.grad_hess_f(z, False)
+    eps = 1e-6
+    E = np.eye(nlp.n)
+    gfd = np.array([(nlp.f(z + eps * e) - nlp.f(z - eps * e)) / (2 * eps) for e in E])
+    assert np.max(np.abs(g - gfd)) <= 1e-6 * np.max(np.abs(g))
+    Jfd = np.array([(nlp.g(z + eps * e) - nlp.g(z - eps * e)) / (2 * eps) for e in E]).T
+    assert np.max(np.abs(nlp.jac(z) - Jfd)) <= 1e-7
+    lam = rng.normal(0, 1, nlp.m)
+    gl = lambda zz: 0.7 * nlp.grad_hess_f(zz, False)[0] + nlp.jac(zz).T @ lam  # noqa: E731
+    Hfd = np.array([(gl(z + eps * e) - gl(z - eps * e)) / (2 * eps) for e in E]).T
+    H = nlp.hess_lag(z, lam, 0.7)
+    assert np.max(np.abs(H - Hfd)) <= 1e-6 * np.max(np.abs(H))
+    cases = [((2, 45, -np.pi / 2, 8), 125.78764721, (5.0, 0.0)),
+             ((3, 30, -np.pi / 2 + 0.1, 5), 3143.38671483, (5.0, -0.62521401)),
+             ((ref[48, 0] + 0.3, ref[48, 1] - 0.2, ref[48, 3] + 0.05, 9), 31.61840094, (5.0, -0.68614018))]
+    for s0, f, u0 in cases:
+        s0 = np.array(s0, float)
+        idx = orc.nearest_index(s0[:2], ref[:, :2])
+        pr = orc.Problem(s0=s0, ego_index=idx, ref_v=ref[np.minimum(idx + np.arange(20), 84), 2].copy())
+        r = ipm.solve_ipopt_like(pr)
+        assert r.success and not r.restoration and r.constr_viol <= 1e-6
+        assert np.max(np.abs(r.u0 - np.array(u0))) <= 1e-5 and abs(r.cost - f) <= 1e-7 * f
