@@ -127,7 +127,8 @@ typedef struct MpcCollisionOut {
   uint8_t* is_collide;        /* [B] */
   int32_t* ego_index;         /* [B] */
   int32_t* stop_index;        /* [B]  regenerated stop row, -1 = none */
-  uint8_t* degenerate;        /* [B]  a tested orientation was within 1e-9 of zero (robust vs plain predicate may differ) */
+  uint8_t* degenerate;        /* [B]  a tested orientation was within 1e-9 (relative) of zero without being zero (robust vs plain predicate may differ) */
+  float* conflict_point;      /* [B][M][2]  the intersection point behind each flag (self.conflict_points, pure_mpc.py:656), NaN = None */
 } MpcCollisionOut;
 
 typedef struct MpcHandle MpcHandle;
@@ -175,11 +176,13 @@ MPC_API int mpc_set_warm_start(MpcHandle* h, const float* u_init);
 
 /* Same call with HOST buffers (what a numpy caller holds): obs/ref_speed/weights/reset_mask are
  * copied host->device, actions/status (and is_collide) device->host, inside the call; the latch
- * lives in the handle.  Synchronous.  Returns bytes moved in *h2d_bytes / *d2h_bytes if non-NULL. */
+ * lives in the handle.  col_host (may be NULL, and so may any pointer in it) receives the per-call collision
+ * outputs in HOST arrays of the MpcCollisionOut shapes -- the public attributes a drop-in PureMPC_Agent exposes.
+ * Synchronous.  Returns bytes moved in *h2d_bytes / *d2h_bytes if non-NULL. */
 MPC_API int mpc_predict_host(MpcHandle* h, const float* obs_host, const float* ref_speed_host,
                      const float* weights_host, const uint8_t* reset_mask_host, int B,
                      float* actions_host, int32_t* status_host, uint8_t* is_collide_host,
-                     int64_t* h2d_bytes, int64_t* d2h_bytes);
+                     const MpcCollisionOut* col_host, int64_t* h2d_bytes, int64_t* d2h_bytes);
 
 /* Measurement helpers */
 /* number of this library's kernel launches since mpc_create (bench.py's gpu_launches) */

@@ -54,7 +54,8 @@ class MpcLatchState(C.Structure):
 
 class MpcCollisionOut(C.Structure):
     _fields_ = [("agent_collide", C.c_void_p), ("conflict_index", C.c_void_p), ("is_collide", C.c_void_p),
-                ("ego_index", C.c_void_p), ("stop_index", C.c_void_p), ("degenerate", C.c_void_p)]
+                ("ego_index", C.c_void_p), ("stop_index", C.c_void_p), ("degenerate", C.c_void_p),
+                ("conflict_point", C.c_void_p)]
 
 
 class MpcEnvStep(C.Structure):
@@ -107,7 +108,8 @@ def load() -> C.CDLL:
     lib.mpc_predict.argtypes = [vp, vp, vp, vp, vp, C.POINTER(MpcLatchState), C.c_int, C.POINTER(MpcSolveOut),
                                 C.POINTER(MpcCollisionOut), vp]
     lib.mpc_predict.restype = C.c_int
-    lib.mpc_predict_host.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.mpc_predict_host.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, C.POINTER(MpcCollisionOut), C.POINTER(C.c_int64),
+                                     C.POINTER(C.c_int64)]
     lib.mpc_predict_host.restype = C.c_int
     lib.mpc_set_warm_start.argtypes = [vp, vp]
     lib.mpc_set_warm_start.restype = C.c_int

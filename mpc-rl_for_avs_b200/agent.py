@@ -58,7 +58,7 @@ class BatchedPureMPC:
     def __init__(self, cfg: Dict, vehicles_count: int, max_batch: int, device: Union[int, str, torch.device] = 0,
                  dt: float = 0.1, collision_check: bool = True, literal_no_collision: bool = False,
                  weight_distance: float = 0.0, weight_collision: float = 0.0,
-                 max_iter: int = 100, tol_step: float = 1e-4, reg_min: float = 1e-2,
+                 max_iter: int = 60, tol_step: float = 1e-4, reg_min: float = 1e-2,
                  threads_per_block: int = 0, blocks_per_sm: int = 0, n_starts: int = 0):
         if not torch.cuda.is_available():
             raise RuntimeError("BatchedPureMPC needs a CUDA device (B200, sm_100a); there is no CPU path")
@@ -105,6 +105,7 @@ class BatchedPureMPC:
         self.ego_index = torch.zeros(B, dtype=torch.int32, device=dev)
         self.stop_index = torch.full((B,), -1, dtype=torch.int32, device=dev)
         self.degenerate = torch.zeros(B, dtype=torch.uint8, device=dev)
+        self.conflict_point = torch.full((B, M, 2), float("nan"), dtype=torch.float32, device=dev)
         self.reference_trajectory = torch.from_numpy(reference_path(self.dt)[:, :2].copy()).to(dev)
         self._u_init = None
 
@@ -217,7 +218,7 @@ class BatchedPureMPC:
                                     self.latch_is_collide.data_ptr())
         col = _capi.MpcCollisionOut(self.agent_collide.data_ptr(), self.conflict_index.data_ptr(),
                                     self.is_collide.data_ptr(), self.ego_index.data_ptr(), self.stop_index.data_ptr(),
-                                    self.degenerate.data_ptr())
+                                    self.degenerate.data_ptr(), self.conflict_point.data_ptr())
         out, U = self._solve_out(B, return_controls)
         rc = self._lib.mpc_predict(self._h, obs.data_ptr(), _ptr(rs), _ptr(w), _ptr(rm), C.byref(latch), B,
                                    C.byref(out), C.byref(col), self._stream())
@@ -236,7 +237,7 @@ class BatchedPureMPC:
                                     self.latch_is_collide.data_ptr())
         col = _capi.MpcCollisionOut(self.agent_collide.data_ptr(), self.conflict_index.data_ptr(),
                                     self.is_collide.data_ptr(), self.ego_index.data_ptr(), self.stop_index.data_ptr(),
-                                    self.degenerate.data_ptr())
+                                    self.degenerate.data_ptr(), self.conflict_point.data_ptr())
         rc = self._lib.mpc_prepare(self._h, obs.data_ptr(), _ptr(rs), _ptr(w), _ptr(rm), C.byref(latch), B,
                                    C.byref(col), self._stream())
         _capi.check(self._lib, self._h, rc)
@@ -330,19 +331,31 @@ class BatchedPureMPC:
         return X, c6, tot
 
     def predict_host(self, obs: np.ndarray, ref_speed: Optional[np.ndarray] = None,
-                     weights: Optional[np.ndarray] = None, reset_mask: Optional[np.ndarray] = None):
+                     weights: Optional[np.ndarray] = None, reset_mask: Optional[np.ndarray] = None,
+                     collision_outputs: bool = False):
         """numpy in, numpy out (host<->device copies inside the call): the call a numpy-holding caller of
         the reference makes.  Uses the handle's own latch.  Returns (actions [B,2] f32, status [B] i32,
-        is_collide [B] u8, h2d_bytes, d2h_bytes)."""
+        is_collide [B] u8, h2d_bytes, d2h_bytes); with `collision_outputs` a sixth element: a dict with the per-call
+        collision outputs (agent_collide [B,M], conflict_index [B,M], conflict_point [B,M,2], ego_index [B],
+        stop_index [B], degenerate [B]) -- the public attributes of the reference agent."""
         if not isinstance(obs, np.ndarray):
             raise TypeError(f"Expect observation type np.ndarray, but got {type(obs)}.")
         if obs.ndim != 3 or obs.shape[1:] != (self.vehicles_count, 8):
             raise ValueError(f"Expect observation's shape of (B, {self.vehicles_count}, 8), but got {obs.shape}")
         B = obs.shape[0]
+        if B > self.max_batch:
+            raise ValueError(f"batch {B} exceeds max_batch {self.max_batch}")
         obs = np.ascontiguousarray(obs, dtype=np.float32)
         rs = None if ref_speed is None else np.ascontiguousarray(ref_speed, dtype=np.float32).reshape(-1)
         w = None if weights is None else np.ascontiguousarray(np.asarray(weights, dtype=np.float32).reshape(B, -1)[:, :3])
-        rm = None if reset_mask is None else np.ascontiguousarray(reset_mask, dtype=np.uint8)
+        rm = None if reset_mask is None else np.ascontiguousarray(reset_mask, dtype=np.uint8).reshape(-1)
+        # the C side reads B entries of each: a shorter array would be read past its end
+        if rs is not None and rs.size != B:
+            raise ValueError(f"ref_speed must have {B} entries, got {rs.size}")
+        if w is not None and w.shape != (B, 3):
+            raise ValueError(f"weights must be [{B}, 3], got {w.shape}")
+        if rm is not None and rm.size != B:
+            raise ValueError(f"reset_mask must have {B} entries, got {rm.size}")
         actions = np.empty((B, 2), dtype=np.float32)
         status = np.empty(B, dtype=np.int32)
         iscol = np.empty(B, dtype=np.uint8)
@@ -351,9 +364,19 @@ class BatchedPureMPC:
         def p(a):
             return None if a is None else a.ctypes.data
 
+        col, extra = None, None
+        if collision_outputs:
+            M = max(self.n_obstacles, 1)
+            extra = dict(agent_collide=np.zeros((B, M), np.uint8), conflict_index=np.full((B, M), -1, np.int32),
+                         ego_index=np.zeros(B, np.int32), stop_index=np.full(B, -1, np.int32), degenerate=np.zeros(B, np.uint8),
+                         conflict_point=np.full((B, M, 2), np.nan, np.float32))
+            col = _capi.MpcCollisionOut(p(extra["agent_collide"]), p(extra["conflict_index"]), None, p(extra["ego_index"]),
+                                        p(extra["stop_index"]), p(extra["degenerate"]), p(extra["conflict_point"]))
         rc = self._lib.mpc_predict_host(self._h, p(obs), p(rs), p(w), p(rm), B, p(actions), p(status), p(iscol),
-                                        C.byref(up), C.byref(down))
+                                        None if col is None else C.byref(col), C.byref(up), C.byref(down))
         _capi.check(self._lib, self._h, rc)
+        if collision_outputs:
+            return actions, status, iscol, int(up.value), int(down.value), extra
         return actions, status, iscol, int(up.value), int(down.value)
 
     # ------------------------------------------------------------------ measurement hooks
@@ -396,18 +419,39 @@ class _EnvConfigView:
         self.vehicles_count = int(cfg["observation"]["vehicles_count"])
 
 
+class _VehicleView:
+    """What callers and plots read from `agent.ego_vehicle` / `agent.agent_vehicles` (agents/utils.py:16-40)."""
+
+    def __init__(self, index, row, heading):
+        self.index = index
+        self.is_ego = index == 0
+        self.position = row[1:3]
+        self.vectorized_speed = row[3:5]
+        self.heading = heading
+        self.speed = np.linalg.norm(self.vectorized_speed)
+        self.sinh, self.cosh = row[6], row[7]
+        self.max_acceleration = 3.5
+        self.max_deceleration = -10
+
+
 class PureMPC_Agent:
     """Drop-in for `agents.pure_mpc.PureMPC_Agent` (collision-aware) -- same constructor and
-    `predict` signature, same return types, same two exceptions -- solving on the B200.
+    `predict` signature, same return types, same two exceptions, same public attributes -- solving on the B200.
 
     `env` only needs `.unwrapped.config` (or `.config`) with `simulation_frequency`,
-    `policy_frequency` and `observation.vehicles_count`."""
+    `policy_frequency` and `observation.vehicles_count`.
+
+    Attributes kept up to date by `predict` (read by the reference's scripts, plots and SB3 subclasses):
+    `ego_index`, `is_collide`, `agent_collide`, `conflict_index`, `conflict_points`, `agent_current_locations`,
+    `stop_point`, `last_valid_stop_point`, `collision_memory`, `last_acc`, `ego_vehicle`, `agent_vehicles`,
+    `reference_trajectory`, `reference_states`.  `plot()` / `visualize_predictions()` exist and do nothing:
+    matplotlib rendering is out of scope (`main/run_pure_mpc.py:32` calls `plot()` unconditionally)."""
 
     weight_components = ["speed", "control", "input_diff"]          # agents/pure_mpc.py:15-22
     _collision_check = True
     _literal = False
 
-    def __init__(self, env, cfg: dict, device: Union[int, str] = 0, use_distance_cost: bool = False) -> None:
+    def __init__(self, env, cfg: dict, device: Union[int, str] = 0, use_distance_cost: bool = False, n_starts: int = 0) -> None:
         ev = _EnvConfigView(env)
         self.env = getattr(env, "unwrapped", env)
         self.env_config = self.env.config
@@ -423,12 +467,22 @@ class PureMPC_Agent:
         self.reference_trajectory = self.global_reference_states[:, :2]
         self._solver = BatchedPureMPC(cfg, vehicles_count=self.total_vehicles_count, max_batch=1, device=device,
                                       dt=self.dt, collision_check=self._collision_check,
-                                      literal_no_collision=self._literal,
+                                      literal_no_collision=self._literal, n_starts=n_starts,
                                       weight_distance=float(cfg.get("weight_distance", 0.0)) if use_distance_cost else 0.0)
+        # per-instance state of agents/pure_mpc.py:38-43, :63 (the latch itself lives in the library handle)
+        self.collision_memory = 0
+        self.collision_memory_steps = 10
+        self.memorized_conflict_points = None
+        self.memorized_conflict_indices = None
+        self.last_valid_stop_point = None
+        self.stop_point = None
         self.last_acc = 0
         self.is_collide = False
         self.ego_index = 0
         self.status = 0
+        self.agent_collide, self.conflict_index, self.conflict_points = [], [], []
+        self.agent_current_locations, self.agent_vehicles, self.ego_vehicle = [], [], None
+        self.observed_vehicles_count = 0
 
     def __str__(self) -> str:
         return "Pure MPC agent [Receding Horizon Control], solved by batched DDP on B200"
@@ -437,6 +491,21 @@ class PureMPC_Agent:
     def reference_states(self):
         return reference_path(self.dt)
 
+    @staticmethod
+    def normalize_angle(angle):
+        """agents/base_agent.py:156-170."""
+        while angle > np.pi:
+            angle -= 2 * np.pi
+        while angle < -np.pi:
+            angle += 2 * np.pi
+        return angle
+
+    def plot(self, *args, **kwargs) -> None:
+        """No-op: the matplotlib debug view of agents/pure_mpc.py:726-804 is out of scope."""
+
+    def visualize_predictions(self, *args, **kwargs) -> None:
+        """No-op: agents/pure_mpc.py:321-457 (matplotlib)."""
+
     def predict(self, obs, return_numpy=True, weights_from_RL=None, ref_speed=None):
         if not isinstance(obs, np.ndarray):
             raise TypeError(f"Expect observation type np.ndarray, but got {type(obs)}.")
@@ -444,11 +513,49 @@ class PureMPC_Agent:
             raise ValueError(f"Expect observation's shape of ({(self.total_vehicles_count, 8)}), but got {obs.shape}")
         rs = None if ref_speed is None else np.asarray(ref_speed, dtype=np.float32).reshape(-1)[:1]
         w = None if weights_from_RL is None else np.asarray(weights_from_RL, dtype=np.float32).reshape(1, -1)
-        actions, status, iscol, _, _ = self._solver.predict_host(obs[None], rs, w)
+        actions, status, iscol, _, _, col = self._solver.predict_host(obs[None], rs, w, collision_outputs=True)
         self.status = int(status[0])
-        if self.status & ~_capi.STATUS_INFEASIBLE_START:
-            print("NOTICE: Not found solution")                      # agents/pure_mpc.py:303-304
+        # what the reference prints when IPOPT reports failure (agents/pure_mpc.py:303-304); the iterate is applied
+        # anyway, as there.  Settling on a kink of the clamped dynamics is not a failure; an infeasible s0 is one there too.
+        if self.status & (_capi.STATUS_MAX_ITER | _capi.STATUS_LINESEARCH_FAIL | _capi.STATUS_NAN | _capi.STATUS_STALLED
+                          | _capi.STATUS_INFEASIBLE_START):
+            print("NOTICE: Not found solution")
+        # ---- public attributes of the reference agent ----------------------------------------------------------------
+        o = np.asarray(obs)
+        n = max(int(np.sum(o[:, 0] == 1)) - 1, 0)
+        n = min(n, self._solver.n_obstacles)
+        self.observed_vehicles_count = n
+        self.ego_vehicle = _VehicleView(0, o[0], self.normalize_angle(o[0, 5]))          # base_agent.py:95-102
+        self.agent_vehicles = [_VehicleView(i + 1, o[i + 1], o[i + 1, 5]) for i in range(n)]
+        self.ego_index = int(col["ego_index"][0])
+        was_latched = self.collision_memory > 0 and self.memorized_conflict_points is not None
         self.is_collide = bool(iscol[0])
+        if self._collision_check:
+            if was_latched:                                        # pure_mpc.py:558-563: memorised values, no detection
+                self.conflict_points = self.memorized_conflict_points
+                self.conflict_index = self.memorized_conflict_indices
+                self.collision_memory -= 1
+            else:
+                self.agent_current_locations = [v.position for v in self.agent_vehicles]
+                self.agent_collide = [bool(x) for x in col["agent_collide"][0, :n]]
+                self.conflict_index = [int(c) if f else None for c, f in zip(col["conflict_index"][0, :n], self.agent_collide)]
+                self.conflict_points = [np.asarray(pt, dtype=np.float64) if f else None
+                                        for pt, f in zip(col["conflict_point"][0, :n], self.agent_collide)]
+                if self.is_collide and any(self.agent_collide):    # pure_mpc.py:664-668
+                    self.collision_memory = self.collision_memory_steps
+                    self.memorized_conflict_points = list(self.conflict_points)
+                    self.memorized_conflict_indices = list(self.conflict_index)
+                elif self.collision_memory > 0:
+                    self.collision_memory -= 1
+                else:
+                    self.memorized_conflict_points = None
+                    self.memorized_conflict_indices = None
+            stop = int(col["stop_index"][0])
+            if stop >= 0:                                          # pure_mpc.py:717-722
+                self.stop_point = self.reference_trajectory[stop]
+                self.last_valid_stop_point = self.stop_point
+            elif self.is_collide and self.last_valid_stop_point is not None and ref_speed is None:
+                self.stop_point = self.last_valid_stop_point
         a, d = float(actions[0, 0]), float(actions[0, 1])
         self.last_acc = a
         act = MPC_Action(acceleration=a, steer=d)
@@ -463,8 +570,8 @@ class PureMPC_NoCollision_Agent(PureMPC_Agent):
 
     _collision_check = False
 
-    def __init__(self, env, cfg: dict, device: Union[int, str] = 0, literal: bool = False) -> None:
+    def __init__(self, env, cfg: dict, device: Union[int, str] = 0, literal: bool = False, n_starts: int = 0) -> None:
         self._literal = bool(literal)
         cfg = dict(cfg)
         cfg.setdefault("weight_speed", cfg.get("weight_state", 1.0) if literal else 1.0)   # quirk Q4
-        super().__init__(env, cfg, device)
+        super().__init__(env, cfg, device, n_starts=n_starts)

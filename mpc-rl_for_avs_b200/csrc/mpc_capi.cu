@@ -39,6 +39,8 @@ struct MpcHandle {
   float* d_obs = nullptr; float* d_ref_speed = nullptr; float* d_weights = nullptr; uint8_t* d_reset = nullptr;
   float* d_actions = nullptr; int32_t* d_status = nullptr; int32_t* d_iters = nullptr; float* d_cost = nullptr;
   int32_t* d_mem = nullptr; int32_t* d_memo = nullptr; uint8_t* d_iscol = nullptr;
+  uint8_t* d_flags = nullptr; int32_t* d_cidx = nullptr; int32_t* d_egoidx = nullptr; int32_t* d_stop = nullptr;
+  uint8_t* d_deg = nullptr; float* d_cpt = nullptr;
   cudaStream_t host_stream = nullptr;
   cudaStream_t copy_stream = nullptr;        // uploads of mpc_predict_host
   cudaEvent_t copy_done[kHostChunks] = {};
@@ -79,6 +81,7 @@ MPC_API int mpc_destroy(MpcHandle* h) {
   cudaFree(h->d_obs); cudaFree(h->d_ref_speed); cudaFree(h->d_weights); cudaFree(h->d_reset);
   cudaFree(h->d_actions); cudaFree(h->d_status); cudaFree(h->d_iters); cudaFree(h->d_cost);
   cudaFree(h->d_mem); cudaFree(h->d_memo); cudaFree(h->d_iscol);
+  cudaFree(h->d_flags); cudaFree(h->d_cidx); cudaFree(h->d_egoidx); cudaFree(h->d_stop); cudaFree(h->d_deg); cudaFree(h->d_cpt);
   if (h->host_stream) cudaStreamDestroy(h->host_stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   for (auto e : h->copy_done) if (e) cudaEventDestroy(e);
@@ -126,7 +129,7 @@ MPC_API int mpc_create(const MpcConfig* cfg, int device, int max_batch, MpcHandl
   s.N = N; s.M = M; s.dt = cfg->dt;
   s.w_distance = cfg->weight_distance; s.w_collision = cfg->weight_collision;
   s.literal_no_collision = cfg->literal_no_collision;
-  s.max_iter = cfg->max_iter > 0 ? cfg->max_iter : 100;
+  s.max_iter = cfg->max_iter > 0 ? cfg->max_iter : 60;
   s.tol_step = cfg->tol_step > 0.f ? cfg->tol_step : 1e-4f;
   s.reg_min = cfg->reg_min > 0.f ? cfg->reg_min : 1e-2f;
   s.stall_tol = 0.f;
@@ -216,6 +219,15 @@ MPC_API int mpc_create(const MpcConfig* cfg, int device, int max_batch, MpcHandl
   CKC(cudaMalloc(&h->d_mem, B * 4));
   CKC(cudaMalloc(&h->d_memo, B * 4));
   CKC(cudaMalloc(&h->d_iscol, B));
+  {
+    const size_t Mx = (size_t)(M > 0 ? M : 1);
+    CKC(cudaMalloc(&h->d_flags, B * Mx));
+    CKC(cudaMalloc(&h->d_cidx, B * Mx * 4));
+    CKC(cudaMalloc(&h->d_egoidx, B * 4));
+    CKC(cudaMalloc(&h->d_stop, B * 4));
+    CKC(cudaMalloc(&h->d_deg, B));
+    CKC(cudaMalloc(&h->d_cpt, B * Mx * 8));
+  }
   CKC(cudaMemset(h->d_mem, 0, B * 4));
   CKC(cudaMemset(h->d_memo, 0xff, B * 4));
   CKC(cudaMemset(h->d_iscol, 0, B));
@@ -388,7 +400,7 @@ MPC_API int mpc_predict(MpcHandle* h, const float* obs, const float* ref_speed, 
 
 MPC_API int mpc_predict_host(MpcHandle* h, const float* obs_host, const float* ref_speed_host, const float* weights_host,
                      const uint8_t* reset_mask_host, int B, float* actions_host, int32_t* status_host,
-                     uint8_t* is_collide_host, int64_t* h2d_bytes, int64_t* d2h_bytes) {
+                     uint8_t* is_collide_host, const MpcCollisionOut* col_host, int64_t* h2d_bytes, int64_t* d2h_bytes) {
   if (!h) return MPC_ERR_BAD_ARG;
   if (B == 0) return MPC_OK;
   if (!obs_host || !actions_host || B < 0) return fail(h, MPC_ERR_BAD_ARG, "mpc_predict_host: null obs/actions or B < 0");
@@ -401,6 +413,14 @@ MPC_API int mpc_predict_host(MpcHandle* h, const float* obs_host, const float* r
   MpcLatchState latch{h->d_mem, h->d_memo, h->d_iscol};
   MpcSolveOut out{h->d_actions, h->d_status, h->d_iters, h->d_cost, nullptr};
   MpcCollisionOut col{};
+  if (col_host) {            // device staging for the outputs the caller asked for
+    if (col_host->agent_collide) col.agent_collide = h->d_flags;
+    if (col_host->conflict_index) col.conflict_index = h->d_cidx;
+    if (col_host->ego_index) col.ego_index = h->d_egoidx;
+    if (col_host->stop_index) col.stop_index = h->d_stop;
+    if (col_host->degenerate) col.degenerate = h->d_deg;
+    if (col_host->conflict_point) col.conflict_point = h->d_cpt;
+  }
   const float* d_rs = ref_speed_host ? h->d_ref_speed : nullptr;
   const float* d_w = weights_host ? h->d_weights : nullptr;
   const uint8_t* d_rm = reset_mask_host ? h->d_reset : nullptr;
@@ -430,6 +450,21 @@ MPC_API int mpc_predict_host(MpcHandle* h, const float* obs_host, const float* r
   CK(h, cudaMemcpyAsync(actions_host, h->d_actions, (size_t)B * 8, cudaMemcpyDeviceToHost, st)); down += (int64_t)B * 8;
   if (status_host) { CK(h, cudaMemcpyAsync(status_host, h->d_status, (size_t)B * 4, cudaMemcpyDeviceToHost, st)); down += (int64_t)B * 4; }
   if (is_collide_host) { CK(h, cudaMemcpyAsync(is_collide_host, h->ws.is_collide, (size_t)B, cudaMemcpyDeviceToHost, st)); down += B; }
+  if (col_host) {
+    const size_t Mx = (size_t)(h->scfg.M > 0 ? h->scfg.M : 1);
+    auto back = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
+      if (!dst) return cudaSuccess;
+      down += (int64_t)bytes;
+      return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st);
+    };
+    CK(h, back(col_host->agent_collide, h->d_flags, (size_t)B * Mx));
+    CK(h, back(col_host->conflict_index, h->d_cidx, (size_t)B * Mx * 4));
+    CK(h, back(col_host->ego_index, h->d_egoidx, (size_t)B * 4));
+    CK(h, back(col_host->stop_index, h->d_stop, (size_t)B * 4));
+    CK(h, back(col_host->degenerate, h->d_deg, (size_t)B));
+    CK(h, back(col_host->conflict_point, h->d_cpt, (size_t)B * Mx * 8));
+    if (col_host->is_collide) CK(h, back(col_host->is_collide, h->ws.is_collide, (size_t)B));
+  }
   CK(h, cudaStreamSynchronize(st));
   if (h2d_bytes) *h2d_bytes = up;
   if (d2h_bytes) *d2h_bytes = down;

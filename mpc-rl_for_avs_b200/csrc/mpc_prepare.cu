@@ -111,14 +111,21 @@ k_prepare(const PrepareParams P) {
   // ---- this lane's other vehicle ---------------------------------------------------------------
   const bool has_veh = l < n_obs;
   double ox = 0, oy = 0, incx = 0, incy = 0;
+  float tinx = 0.f, tiny = 0.f;                        // float32 increments of the collision-check track
   if (has_veh) {
     const float* r = ob + (size_t)(l + 1) * 8;
     ox = r[1]; oy = r[2];
     const double sp = norm2((double)r[3], (double)r[4]);
     const double hd = r[5];                            // NOT wrapped, base_agent.py:112
     const double sd = sp * P.dt;                       // speed * dt * (cos, sin), base_agent.py:172-174
-    incx = sd * cos(hd);
-    incy = sd * sin(hd);
+    const double ch = cos(hd), sh = sin(hd);
+    incx = sd * ch;
+    incy = sd * sh;
+    // predict_future_positions (agents/pure_mpc.py:543-550) runs in float32 under the reference's pinned numpy 2.1.2:
+    // float32 position + float32(speed) * float32(dt) * float32(cos, sin), see oracle predict_other_polyline
+    const float sdf = (float)sp * (float)P.dt;
+    tinx = sdf * (float)ch;
+    tiny = sdf * (float)sh;
   }
 
   // ---- latch (agents/pure_mpc.py:558-563) -----------------------------------------------------
@@ -132,6 +139,7 @@ k_prepare(const PrepareParams P) {
   }
   const bool latched = P.collision_check && mem > 0 && memo >= 0;
   int my_flag = 0, my_cidx = -1, my_deg = 0;
+  double my_qx = 0.0, my_qy = 0.0;
   int cmin = -1;
   int stop_index = -1;
   bool aborted = false;
@@ -188,11 +196,40 @@ k_prepare(const PrepareParams P) {
     if (!aborted && has_veh) {
       // ---- intersections of the ego polyline with this vehicle's straight 31-point track ------
       double Ox[kPred + 1], Oy[kPred + 1];
-      Ox[0] = ox; Oy[0] = oy;
-      for (int t = 1; t <= kPred; ++t) { Ox[t] = Ox[t - 1] + incx; Oy[t] = Oy[t - 1] + incy; }
+      {
+        float fx = (float)ox, fy = (float)oy;            // exact: the observation is float32
+        Ox[0] = ox; Oy[0] = oy;
+        for (int t = 1; t <= kPred; ++t) { fx = fx + tinx; fy = fy + tiny; Ox[t] = fx; Oy[t] = fy; }
+      }
       bool have = false;
       double qx = 0, qy = 0;
       const double tlen = fabs(Ox[kPred] - Ox[0]) + fabs(Oy[kPred] - Oy[0]);
+      // nearest-time test of a candidate point (agents/pure_mpc.py:641-649), first minimum wins
+      auto time_test = [&](double cx, double cy) -> bool {
+        int te = 0, to = 0;
+        double bde = 1e300, bdo = 1e300;
+        for (int t = 0; t < ne; ++t) { double d = dist2(s_ex[g][t] - cx, s_ey[g][t] - cy); if (d < bde) { bde = d; te = t; } }
+        for (int t = 0; t <= kPred; ++t) { double d = dist2(Ox[t] - cx, Oy[t] - cy); if (d < bdo) { bdo = d; to = t; } }
+        int dtm = te - to; dtm = dtm < 0 ? -dtm : dtm;
+        return dtm < kTimeThreshold;
+      };
+      // collinear overlaps (the same-lane case: the lane centre x = 2.0 is the path's own x): GEOS returns a LineString
+      // per connected overlap and the reference takes its middle coordinate (agents/pure_mpc.py:618-622, :628-633)
+      constexpr int kMaxPieces = 4, kMaxPts = 8;
+      double plo[kMaxPieces], phi[kMaxPieces];
+      int psg[kMaxPieces], npieces = 0;
+      double ptx[kMaxPts], pty[kMaxPts];
+      int npts = 0;
+      const bool axx = fabs(Ox[kPred] - Ox[0]) >= fabs(Oy[kPred] - Oy[0]);   // scalar coordinate along the track: dominant axis
+      const double o_a = axx ? Ox[0] : Oy[0], o_b = axx ? Ox[kPred] : Oy[kPred];
+      const double olo = fmin(o_a, o_b), ohi = fmax(o_a, o_b);
+      auto add_point = [&](double cx, double cy) {        // every intersection point, for the GeometryCollection test below
+        if (npts < kMaxPts) { ptx[npts] = cx; pty[npts] = cy; ++npts; } else my_deg = 1;
+        if (time_test(cx, cy)) {
+          // candidates are visited in lexicographic (x, y) order: keep the smallest passing one
+          if (!have || cx < qx || (cx == qx && cy < qy)) { have = true; qx = cx; qy = cy; }
+        }
+      };
       for (int i = 0; i + 1 < ne; ++i) {
         const double p1x = s_ex[g][i], p1y = s_ey[g][i], p2x = s_ex[g][i + 1], p2y = s_ey[g][i + 1];
         // orientation of track ends about the ego segment is affine in t: locate the sign change
@@ -206,6 +243,29 @@ k_prepare(const PrepareParams P) {
         const double f1 = orient(Ox[0], Oy[0], Ox[kPred], Oy[kPred], p1x, p1y);
         const double f2 = orient(Ox[0], Oy[0], Ox[kPred], Oy[kPred], p2x, p2y);
         if ((f1 > tol && f2 > tol) || (f1 < -tol && f2 < -tol)) continue;
+        if (e0 == 0.0 && e30 == 0.0 && ohi > olo) {
+          // candidate for "this ego segment lies on the track's line": the oracle asks for all four orientations of
+          // every segment pair to be exactly zero
+          bool allzero = true;
+          for (int j = 0; j < kPred && allzero; ++j) {
+            allzero = orient(Ox[j], Oy[j], Ox[j + 1], Oy[j + 1], p1x, p1y) == 0.0 && orient(Ox[j], Oy[j], Ox[j + 1], Oy[j + 1], p2x, p2y) == 0.0 &&
+                      orient(p1x, p1y, p2x, p2y, Ox[j], Oy[j]) == 0.0 && orient(p1x, p1y, p2x, p2y, Ox[j + 1], Oy[j + 1]) == 0.0;
+          }
+          const double a = axx ? p1x : p1y, b = axx ? p2x : p2y;
+          if (allzero && a != b) {
+            const double lo = fmax(fmin(a, b), olo), hi = fmin(fmax(a, b), ohi);
+            if (hi > lo) {
+              if (npieces > 0 && (plo[npieces - 1] == hi || phi[npieces - 1] == lo)) {
+                plo[npieces - 1] = fmin(plo[npieces - 1], lo); phi[npieces - 1] = fmax(phi[npieces - 1], hi);
+              } else if (npieces < kMaxPieces) {
+                plo[npieces] = lo; phi[npieces] = hi; psg[npieces] = b > a ? 1 : -1; ++npieces;
+              } else {
+                my_deg = 1;
+              }
+            }
+            continue;                                     // handled as an overlap
+          }
+        }
         int jlo = 0, jhi = kPred - 1;
         const double de = e30 - e0;
         if (fabs(de) > tol) {
@@ -226,29 +286,64 @@ k_prepare(const PrepareParams P) {
           const bool proper = (d1 * d2 < 0) && (d3 * d4 < 0);
           if (!proper) {
             if (fabs(d1) <= eps || fabs(d2) <= eps || fabs(d3) <= eps || fabs(d4) <= eps) {
-              // near-touching pair with overlapping boxes: robust and plain predicates may differ
               const bool box = fmin(p1x, p2x) <= fmax(q1x, q2x) + 1e-9 && fmin(q1x, q2x) <= fmax(p1x, p2x) + 1e-9 &&
                                fmin(p1y, p2y) <= fmax(q1y, q2y) + 1e-9 && fmin(q1y, q2y) <= fmax(p1y, p2y) + 1e-9;
-              if (box) my_deg = 1;
+              if (box) {
+                // exact touches (orientation exactly zero, the endpoint inside the other segment's box) are genuine
+                // intersection points; near zero but not zero: robust and plain predicates may differ
+                auto on_seg = [](double px, double py, double sx, double sy, double ex_, double ey_) {
+                  return fmin(sx, ex_) <= px && px <= fmax(sx, ex_) && fmin(sy, ey_) <= py && py <= fmax(sy, ey_);
+                };
+                if (d1 == 0.0 && on_seg(p1x, p1y, q1x, q1y, q2x, q2y)) add_point(p1x, p1y);
+                if (d2 == 0.0 && on_seg(p2x, p2y, q1x, q1y, q2x, q2y)) add_point(p2x, p2y);
+                if (d3 == 0.0 && on_seg(q1x, q1y, p1x, p1y, p2x, p2y)) add_point(q1x, q1y);
+                if (d4 == 0.0 && on_seg(q2x, q2y, p1x, p1y, p2x, p2y)) add_point(q2x, q2y);
+                if ((d1 != 0.0 && fabs(d1) <= eps) || (d2 != 0.0 && fabs(d2) <= eps) || (d3 != 0.0 && fabs(d3) <= eps) || (d4 != 0.0 && fabs(d4) <= eps)) my_deg = 1;
+              }
             }
             continue;
           }
           const double tt = d1 / (d1 - d2);
-          const double cx = p1x + tt * (p2x - p1x), cy = p1y + tt * (p2y - p1y);
-          // nearest-time test (agents/pure_mpc.py:641-649), first minimum wins
-          int te = 0, to = 0;
-          double bde = 1e300, bdo = 1e300;
-          for (int t = 0; t < ne; ++t) { double d = dist2(s_ex[g][t] - cx, s_ey[g][t] - cy); if (d < bde) { bde = d; te = t; } }
-          for (int t = 0; t <= kPred; ++t) { double d = dist2(Ox[t] - cx, Oy[t] - cy); if (d < bdo) { bdo = d; to = t; } }
-          int dtm = te - to; dtm = dtm < 0 ? -dtm : dtm;
-          if (dtm < kTimeThreshold) {
-            // candidates are visited in lexicographic (x, y) order: keep the smallest passing one
-            if (!have || cx < qx || (cx == qx && cy < qy)) { have = true; qx = cx; qy = cy; }
-          }
+          add_point(p1x + tt * (p2x - p1x), p1y + tt * (p2y - p1y));
+        }
+      }
+      if (npieces > 0) {
+        // isolated points that are not part of an overlap make the result a GeometryCollection, for which the
+        // reference's dispatch has no branch: no candidate at all
+        have = false;
+        bool mixed = false;
+        for (int k = 0; k < npts; ++k) {
+          const double c = axx ? ptx[k] : pty[k];
+          bool inside = false;
+          for (int q = 0; q < npieces; ++q) inside = inside || (plo[q] <= c && c <= phi[q]);
+          if (!inside || orient(Ox[0], Oy[0], Ox[kPred], Oy[kPred], ptx[k], pty[k]) != 0.0) mixed = true;
+        }
+        for (int q = 0; q < npieces && !mixed && !have; ++q) {
+          // merged vertices of both polylines inside the overlap, ordered along the ego polyline (stable: ego vertices
+          // first), one per position; the reference takes coords[len // 2]
+          double key[2 * (kPred + 1)], vx[2 * (kPred + 1)], vy[2 * (kPred + 1)];
+          int n = 0;
+          auto insert = [&](double px, double py) {
+            const double c = axx ? px : py;
+            if (!(plo[q] <= c && c <= phi[q])) return;
+            const double kk = psg[q] * c;
+            int pos = n;
+            while (pos > 0 && key[pos - 1] > kk) --pos;   // after the entries with an equal key (stable)
+            for (int m = n; m > pos; --m) { key[m] = key[m - 1]; vx[m] = vx[m - 1]; vy[m] = vy[m - 1]; }
+            key[pos] = kk; vx[pos] = px; vy[pos] = py; ++n;
+          };
+          for (int t = 0; t < ne; ++t)
+            if (orient(Ox[0], Oy[0], Ox[kPred], Oy[kPred], s_ex[g][t], s_ey[g][t]) == 0.0) insert(s_ex[g][t], s_ey[g][t]);
+          for (int t = 0; t <= kPred; ++t) insert(Ox[t], Oy[t]);
+          int m = 0;                                      // drop repeated positions (keep the first)
+          for (int k = 0; k < n; ++k)
+            if (k == 0 || key[k] != key[m - 1]) { key[m] = key[k]; vx[m] = vx[k]; vy[m] = vy[k]; ++m; }
+          if (m > 0 && time_test(vx[m / 2], vy[m / 2])) { have = true; qx = vx[m / 2]; qy = vy[m / 2]; }
         }
       }
       if (have) {
         my_flag = 1;
+        my_qx = qx; my_qy = qy;
         double bdr = 1e300;
         for (int j = 0; j < kNRef; ++j) { double d = dist2(s_ref[j][0] - qx, s_ref[j][1] - qy); if (d < bdr) { bdr = d; my_cidx = j; } }
       }
@@ -285,6 +380,11 @@ k_prepare(const PrepareParams P) {
   if (l < P.M) {
     if (P.col.agent_collide) P.col.agent_collide[(size_t)b * P.M + l] = (uint8_t)((P.collision_check && !latched && !aborted) ? my_flag : 0);
     if (P.col.conflict_index) P.col.conflict_index[(size_t)b * P.M + l] = (P.collision_check && !latched && !aborted && my_flag) ? my_cidx : -1;
+    if (P.col.conflict_point) {
+      const bool hit = P.collision_check && !latched && !aborted && my_flag;
+      P.col.conflict_point[((size_t)b * P.M + l) * 2] = hit ? (float)my_qx : nanf("");
+      P.col.conflict_point[((size_t)b * P.M + l) * 2 + 1] = hit ? (float)my_qy : nanf("");
+    }
     float* O = P.ws.obstacles;
     const size_t B = P.B;
     O[((size_t)l * 4 + 0) * B + b] = has_veh ? (float)ox : 0.f;

@@ -37,7 +37,7 @@ _LANE_HEADING = np.array([-math.pi / 2, 0.0, math.pi / 2, math.pi])
 
 
 def make_scenarios(batch: int, n_obstacles: int = 8, seed: int = 1234, vehicles_count: Optional[int] = None,
-                   ref_speed_fraction: float = 0.5, v_max: float = 12.0
+                   ref_speed_fraction: float = 0.5, v_max: float = 12.0, same_lane_frac: float = 0.0
                    ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """Returns (obs [B,V,8] f32, ref_speed [B,1] f32, has_ref_speed [B] bool) on the CPU.
 
@@ -46,6 +46,10 @@ def make_scenarios(batch: int, n_obstacles: int = 8, seed: int = 1234, vehicles_
     c ~ U{0..3}, position R_c (2 + N(0, 0.2^2), d), d ~ U(-30, 70), speed max(0.5, N(8, 1)),
     lane heading; samples closer than 5 m to the ego are redrawn.  `ref_speed` ~ U(0, 15) for the
     flagged fraction of the batch (RL v0 mode), unused elsewhere.
+    `same_lane_frac` > 0 (tests): in that fraction of the scenes the first other vehicle sits EXACTLY on the ego's lane
+    centre x = 2.0 with heading -pi/2 (highway-env spawns on the lane centre, which is the reference path's own x) --
+    the collinear / LineString branch of the reference's collision check (agents/pure_mpc.py:615-633).  Drawn from a
+    separate stream so the default scenes do not change.
     """
     g = torch.Generator(device="cpu")
     g.manual_seed(int(seed))
@@ -98,6 +102,17 @@ def make_scenarios(batch: int, n_obstacles: int = 8, seed: int = 1234, vehicles_
 
     has = rand(B) < ref_speed_fraction
     rs = 15.0 * rand(B)
+    if M > 0 and same_lane_frac > 0.0:
+        g2 = torch.Generator(device="cpu")
+        g2.manual_seed(int(seed) + 99991)
+        pick = torch.rand(B, generator=g2, dtype=torch.float64).numpy() < same_lane_frac
+        off = 6.0 + 30.0 * torch.rand(B, generator=g2, dtype=torch.float64).numpy()
+        ahead = torch.rand(B, generator=g2, dtype=torch.float64).numpy() < 0.8
+        y = np.where(ahead, ey - off, ey + off)              # ahead = further along the path's first leg (decreasing y)
+        sp = spd[:, 0]
+        hd32 = float(np.float32(-math.pi / 2))
+        for k, v in ((1, 2.0), (2, y), (3, sp * math.cos(hd32)), (4, sp * math.sin(hd32)), (5, hd32), (6, math.sin(hd32)), (7, math.cos(hd32))):
+            obs[:, 1, k] = np.where(pick, v, obs[:, 1, k])
     return (torch.from_numpy(obs.astype(np.float32)),
             torch.from_numpy(rs.astype(np.float32)).reshape(B, 1),
             torch.from_numpy(has))

@@ -22,8 +22,11 @@ segment intersection).  Against those outputs this module is
     regenerated speeds, 1.3e-4 relative on the archive's obstacle-distance term -- all of it one
     quirk (Q11): under the reference's pinned numpy 2.x, np.float32 scalars stay float32 against
     Python floats (NEP 50), so the reference carries the ego speed, a wrapped heading and the other
-    vehicles' predicted positions in float32; this module uses float64 on the exact float32 inputs
-    (what the same reference computes under numpy 1.x promotion);
+    vehicles' in-NLP predicted positions in float32; this module uses float64 on the exact float32 inputs
+    (what the same reference computes under numpy 1.x promotion).  The one place where that choice would
+    change a DISCRETE output is kept in float32 like the reference: the other vehicles' 31-point tracks of
+    the collision check (predict_other_polyline), where float32 accumulation keeps a same-lane vehicle
+    exactly on the path's line;
   * identical bounds, cold start and dynamics constraints (the rollout below zeroes the reference's g).
 STILL UNPINNED: GEOS' intersection primitive (incl. the order of MultiPoint members: assumed
 lexicographic) and which local optimum IPOPT returns from the cold start.  For the latter the NLP is
@@ -540,12 +543,24 @@ def predict_ego_polyline(pos: np.ndarray, speed: float, start_index: int, ref_sp
 
 
 def predict_other_polyline(p: Sequence[float], speed: float, heading: float, dt: float = 0.1) -> np.ndarray:
-    """31 points by repeated addition of speed*dt*(cos h, sin h) (agents/pure_mpc.py:529-550)."""
-    inc = speed * dt * np.array([np.cos(heading), np.sin(heading)])
-    pts = [np.array(p, dtype=np.float64)]
+    """31 points by repeated addition of speed*dt*(cos h, sin h) (agents/pure_mpc.py:529-550) -- in FLOAT32, as the
+    reference computes them: under its pinned numpy 2.1.2 (requirements.txt:1, NEP 50) `position` is a float32 slice of
+    the observation, `speed` = np.linalg.norm of a float32 slice and `heading` a float32 scalar, and
+    `future_positions[-1] + speed * dt * np.array([np.cos(heading), np.sin(heading)])` stays float32 throughout.  This
+    is decisive for same-lane traffic: x = 2.0 + 30 tiny float32 increments stays EXACTLY 2.0 -- the track is collinear
+    with the path and the LineString branch of pure_mpc.py:618-622 is taken -- whereas float64 accumulation drifts off
+    the line by ~1e-6 m.  (`speed` arrives here as the float64 norm and is rounded once; numpy's float32 norm may
+    differ from that by one ulp.)"""
+    f = np.float32
+    sd = f(speed) * f(dt)
+    h = f(heading)
+    inc = sd * np.array([np.cos(h), np.sin(h)], dtype=np.float32)
+    cur = np.array(p, dtype=np.float32)
+    pts = [cur]
     for _ in range(PRED_HORIZON):
-        pts.append(pts[-1] + inc)
-    return np.array(pts)
+        cur = cur + inc
+        pts.append(cur)
+    return np.array(pts, dtype=np.float64)
 
 
 def _orient(ax, ay, bx, by, cx, cy):
@@ -645,7 +660,8 @@ def polyline_intersections(E: np.ndarray, O: np.ndarray, degenerate_eps: float =
         for lo, hi, sgn in pieces:
             vs = [tuple(v) for v in E if lo <= v[ax] <= hi and _orient(O0[0], O0[1], O1[0], O1[1], v[0], v[1]) == 0]
             vs += [tuple(v) for v in O if lo <= v[ax] <= hi]
-            vs = sorted(set(vs), key=lambda v: sgn * v[ax])
+            vs = sorted(vs, key=lambda v: sgn * v[ax])              # stable: ego vertices before track vertices
+            vs = [v for k, v in enumerate(vs) if k == 0 or v[ax] != vs[k - 1][ax]]   # one vertex per position on the line
             mids.append(vs[len(vs) // 2])
         return np.array(mids, dtype=np.float64), degenerate
     if not pts:

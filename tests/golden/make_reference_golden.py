@@ -131,10 +131,39 @@ class _Empty:
     coords = []
 
 
+class _Line:
+    geom_type = "LineString"
+    is_empty = False
+
+    def __init__(self, coords):
+        self.coords = list(coords)
+
+
+class _MultiLine:
+    geom_type = "MultiLineString"
+    is_empty = False
+
+    def __init__(self, lines):
+        self.geoms = [_Line(c) for c in lines]
+
+
+class _Collection:
+    geom_type = "GeometryCollection"          # pure_mpc.py:615-633 has no branch for it
+    is_empty = False
+
+    def __init__(self, geoms):
+        self.geoms = geoms
+
+
 DEGENERATE = {"flag": False}
 
 
 class LineString:
+    """Stand-in for shapely.geometry.LineString: textbook parametric segment intersection.  Collinear overlaps are
+    noded like an overlay would (every vertex of either line inside the overlap becomes a coordinate of the result) and
+    chained along `self`; exact vertex touches are points; anything within 1e-9 of a vertex without being exact marks the
+    scene as predicate-dependent (dropped from the fixture)."""
+
     def __init__(self, coords):
         pts = [np.asarray(c, dtype=np.float64) for c in coords]
         if len(pts) == 1:
@@ -143,6 +172,7 @@ class LineString:
 
     def intersection(self, other):
         out = []
+        edges = []                                          # noded collinear sub-segments, as (a, b) vertex tuples along self
         for i in range(len(self.pts) - 1):
             p, r = self.pts[i], self.pts[i + 1] - self.pts[i]
             for j in range(len(other.pts) - 1):
@@ -150,17 +180,57 @@ class LineString:
                 den = r[0] * s[1] - r[1] * s[0]
                 qp = q - p
                 if den == 0.0:
-                    if qp[0] * r[1] - qp[1] * r[0] == 0.0 and (r @ r > 0 or s @ s > 0):
-                        DEGENERATE["flag"] = True          # collinear: GEOS may return a LineString; scene dropped
+                    if qp[0] * r[1] - qp[1] * r[0] == 0.0 and r @ r > 0 and s @ s > 0:
+                        # collinear: overlap of [p, p+r] and [q, q+s] measured along r; the overlap's ends are two of the
+                        # four vertices
+                        four = [(0.0, tuple(self.pts[i])), (1.0, tuple(self.pts[i + 1])),
+                                (float(qp @ r) / float(r @ r), tuple(other.pts[j])),
+                                (float((qp + s) @ r) / float(r @ r), tuple(other.pts[j + 1]))]
+                        lo = max(0.0, min(four[2][0], four[3][0]))
+                        hi = min(1.0, max(four[2][0], four[3][0]))
+                        if hi > lo:
+                            ends = sorted([f for f in four if lo <= f[0] <= hi], key=lambda f: f[0])
+                            edges.append((ends[0][1], ends[-1][1]))
+                        elif hi == lo:
+                            out.append([f[1] for f in four if f[0] == lo][0])
+                    elif r @ r == 0 or s @ s == 0:
+                        DEGENERATE["flag"] = True          # zero-length segment: scene dropped
                     continue
                 t = (qp[0] * s[1] - qp[1] * s[0]) / den
                 u = (qp[0] * r[1] - qp[1] * r[0]) / den
                 eps = 1e-9
                 if -eps <= t <= 1 + eps and -eps <= u <= 1 + eps:
-                    if min(abs(t), abs(t - 1), abs(u), abs(u - 1)) < 1e-9:
-                        DEGENERATE["flag"] = True          # through a vertex: predicate-dependent; scene dropped
-                    out.append((float(p[0] + t * r[0]), float(p[1] + t * r[1])))
-        uniq = sorted(set(out))
+                    if t in (0.0, 1.0) and 0.0 <= u <= 1.0:
+                        out.append(tuple(self.pts[i] if t == 0.0 else self.pts[i + 1]))      # exact vertex touch
+                    elif u in (0.0, 1.0) and 0.0 <= t <= 1.0:
+                        out.append(tuple(other.pts[j] if u == 0.0 else other.pts[j + 1]))
+                    elif min(abs(t), abs(t - 1), abs(u), abs(u - 1)) < 1e-9:
+                        DEGENERATE["flag"] = True          # next to a vertex: predicate-dependent; scene dropped
+                    else:
+                        out.append((float(p[0] + t * r[0]), float(p[1] + t * r[1])))
+        lines = []
+        for a, b in edges:                                  # chain the noded edges in the order of `self`
+            if lines and lines[-1][-1] == a:
+                lines[-1].append(b)
+            elif lines and a in lines[-1] and b in lines[-1]:
+                pass
+            else:
+                lines.append([a, b])
+        # the sub-segments of one overlap arrive once per (i, j) pair: restore every vertex in between
+        merged = []
+        for ln in lines:
+            lo_, hi_ = ln[0], ln[-1]
+            d = np.subtract(hi_, lo_)
+            along = lambda v: float(np.subtract(v, lo_) @ d)  # noqa: E731
+            verts = {tuple(v) for v in self.pts + other.pts
+                     if (v[0] - lo_[0]) * d[1] - (v[1] - lo_[1]) * d[0] == 0.0 and 0.0 <= along(v) <= along(hi_)}
+            merged.append(sorted(verts, key=along))
+        on_line = lambda pt: any(pt in ln for ln in merged)  # noqa: E731
+        uniq = sorted({pt for pt in out if not on_line(pt)})
+        if merged and uniq:
+            return _Collection([_Point(*u_) for u_ in uniq] + [_Line(c) for c in merged])
+        if merged:
+            return _Line(merged[0]) if len(merged) == 1 else _MultiLine(merged)
         if not uniq:
             return _Empty()
         return _Point(*uniq[0]) if len(uniq) == 1 else _Multi(uniq)
@@ -262,6 +332,13 @@ def main():
     obs_all[1, 5:, 0] = 0.0
     obs_all[2, 0, 5] += 2 * np.pi
     obs_all[3, 0, 3:5] = 0.0
+    # same-lane traffic: every fourth scene gets one or two vehicles exactly on the lane centre x = 2.0 (the path's own x)
+    # heading -pi/2, ahead of or behind the ego -- the collinear / LineString branch of pure_mpc.py:615-633
+    for i in range(4, S, 4):
+        for m in (1, 2)[: 1 + (i // 4) % 2]:
+            sp = float(rng.uniform(2.0, 9.0))
+            y = float(np.float32(obs_all[i, 0, 2] + rng.uniform(-25.0, 25.0)))
+            obs_all[i, m] = (1.0, 2.0, y, np.float32(sp * np.cos(-np.pi / 2)), -sp, -np.pi / 2, -1.0, np.float32(np.cos(-np.pi / 2)))
     keep, rec = [], []
     for i in range(S):
         ag = make_agent(ref_mpc, V, N)
@@ -318,6 +395,8 @@ def main():
     Q, T = 24, 16
     obs0, _, _ = pkg.make_scenarios(Q, M, seed=777)
     obs0 = obs0.numpy()
+    for q in range(0, Q, 3):                                # a lead vehicle on the ego's own lane centre in every third sequence
+        obs0[q, 1] = (1.0, 2.0, np.float32(20.0 + q), np.float32(5.0 * np.cos(-np.pi / 2)), -5.0, -np.pi / 2, -1.0, np.float32(np.cos(-np.pi / 2)))
     path = pkg.reference_path(0.1)
     seq_obs = np.zeros((Q, T, V, 8), np.float32)
     seq = {k: [] for k in ("is_collide", "memory", "ego_index", "ref_v", "flags", "cidx")}

@@ -101,7 +101,7 @@ class HsBatch(C.Structure):
                 ("is_collide", _P(C.c_ubyte)), ("n_obs", _P(C.c_int)), ("obstacles", _P(C.c_float))]
 
 
-def hs_config(N=20, M=8, dt=0.1, w_distance=0.0, w_collision=0.0, literal=0, max_iter=100, tol_step=1e-4, reg_min=1e-2, stall_tol=0.0, kink_tol=1e-7):
+def hs_config(N=20, M=8, dt=0.1, w_distance=0.0, w_collision=0.0, literal=0, max_iter=60, tol_step=1e-4, reg_min=1e-2, stall_tol=0.0, kink_tol=1e-7):
     return HsConfig(N=N, M=M, dt=dt, w_distance=w_distance, w_collision=w_collision, literal_no_collision=literal,
                     max_iter=max_iter, tol_step=tol_step, reg_min=reg_min, stall_tol=stall_tol, kink_tol=kink_tol)
 
@@ -225,10 +225,10 @@ def solve_parity_stats(r, g, probs):
 # measured on the host build of the device code and on the B200 (tools/solve_parity_report.py); thresholds sit a
 # little below the measured rates.  Keys: (golden set, n_starts).
 PARITY_BARS = {
-    ("golden_track", 4): dict(in_path=dict(settled=0.98, conv=0.96, below=0.96, same=0.91), all=dict(settled=0.98, below=0.93, same=0.86)),
-    ("golden_coll", 4): dict(in_path=dict(settled=0.96, conv=0.95, below=0.97, same=0.91), all=dict(settled=0.95, below=0.93, same=0.86)),
-    ("golden_track", 1): dict(in_path=dict(settled=0.99, conv=0.98, below=0.92, same=0.90), all=dict(settled=0.98, below=0.85, same=0.83)),
-    ("golden_coll", 1): dict(in_path=dict(settled=0.94, conv=0.93, below=0.88, same=0.87), all=dict(settled=0.93, below=0.83, same=0.83)),
+    ("golden_track", 4): dict(in_path=dict(settled=0.96, conv=0.95, below=0.96, same=0.91), all=dict(settled=0.96, below=0.93, same=0.86)),
+    ("golden_coll", 4): dict(in_path=dict(settled=0.96, conv=0.95, below=0.97, same=0.91), all=dict(settled=0.93, below=0.93, same=0.86)),
+    ("golden_track", 1): dict(in_path=dict(settled=0.95, conv=0.95, below=0.92, same=0.90), all=dict(settled=0.95, below=0.85, same=0.83)),
+    ("golden_coll", 1): dict(in_path=dict(settled=0.91, conv=0.91, below=0.88, same=0.87), all=dict(settled=0.91, below=0.83, same=0.83)),
 }
 
 

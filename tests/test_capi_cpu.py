@@ -31,7 +31,7 @@ def test_struct_layouts_match_the_header():
     assert C.sizeof(capi.MpcProblemBatch) == 12 * C.sizeof(C.c_void_p)
     assert C.sizeof(capi.MpcSolveOut) == 5 * C.sizeof(C.c_void_p)
     assert C.sizeof(capi.MpcLatchState) == 3 * C.sizeof(C.c_void_p)
-    assert C.sizeof(capi.MpcCollisionOut) == 6 * C.sizeof(C.c_void_p)
+    assert C.sizeof(capi.MpcCollisionOut) == 7 * C.sizeof(C.c_void_p)
 
 
 def test_create_rejects_bad_arguments_and_missing_device():

@@ -109,8 +109,35 @@ def test_collision_geometry_and_regeneration():
     assert res.agent_collide == [True] and not res.degenerate
     assert res.conflict_index[0] == orc.nearest_index((2.0, 25.4), ref[:, :2]) == 24
     assert np.allclose(res.conflict_points[0], (2.0, 25.4))
-    # a crossing exactly through an ego polyline vertex is flagged degenerate (robust predicates could differ)
-    assert orc.detect_collisions(ego, np.array([[-10.0, 25.0, 8.0, 0.0]])).degenerate
+    # a crossing exactly through an ego polyline vertex (orientation exactly zero) is a genuine point, not degenerate
+    res = orc.detect_collisions(ego, np.array([[-10.0, 25.0, 8.0, 0.0]]))
+    assert res.agent_collide == [True] and not res.degenerate and np.allclose(res.conflict_points[0], (2.0, 25.0))
+    # ... a hair off the vertex is: robust and plain predicates could differ
+    Ee = orc.predict_ego_polyline(ego[:2], 10.0, 9, 10.0)
+    Oo = orc.predict_other_polyline((-10.0, 25.0), 8.0, 0.0) + (0.0, 2e-10)
+    assert orc.polyline_intersections(Ee, Oo)[1]
+    # same lane (agents/pure_mpc.py:618-622): a vehicle exactly on the lane centre x = 2.0 heading -pi/2 -- its float32
+    # track stays on the path's line, GEOS returns the overlap as a LineString and the reference takes coords[len // 2]
+    lead = np.array([[2.0, 30.0, 5.0, float(np.float32(-np.pi / 2))]])
+    res = orc.detect_collisions(np.array([2.03, 45.0, -np.pi / 2, 8.0]), lead)
+    O = orc.predict_other_polyline(lead[0, :2], 5.0, lead[0, 3])
+    assert np.all(O[:, 0] == 2.0) and abs(O[-1, 1] - 15.0) < 1e-4            # exactly on the line, 30 x 0.5 m down
+    assert res.agent_collide == [True] and not res.degenerate
+    E = orc.predict_ego_polyline((2.03, 45.0), 8.0, orc.nearest_index((2.03, 45.0), ref[:, :2]), 10.0)
+    lo, hi = max(E[-1, 1], O[-1, 1]), min(E[1, 1], O[0, 1])                  # overlap of the two spans on x = 2
+    merged = sorted({y for y in E[1:, 1] if lo <= y <= hi} | {y for y in O[:, 1] if lo <= y <= hi}, reverse=True)
+    assert res.conflict_points[0][0] == 2.0 and res.conflict_points[0][1] == merged[len(merged) // 2]
+    # behind the ego: the overlap is empty, nothing is flagged
+    assert orc.detect_collisions(np.array([2.03, 45.0, -np.pi / 2, 8.0]), np.array([[2.0, 70.0, 5.0, lead[0, 3]]])).agent_collide == [False]
+    # an overlap plus an isolated crossing would be a GeometryCollection, which pure_mpc.py:615-633 does not dispatch on
+    O2 = np.array([[1.0, 0.0], [2.0, 0.0], [3.0, 0.0]])
+    E2 = np.array([[0.0, 0.0], [1.5, 0.0], [1.5, 4.0], [2.5, 4.0], [2.5, -4.0]])
+    pts, deg = orc.polyline_intersections(E2, O2)
+    assert len(pts) == 0 and not deg
+    # ... while a crossing ON the overlap belongs to it: LineString, middle of the merged vertices (1, 2, 3, 4 -> index 2)
+    E3 = np.array([[0.0, 0.0], [4.0, 0.0], [4.0, 4.0], [2.0, 4.0], [2.0, -4.0]])
+    pts, deg = orc.polyline_intersections(E3, O2)
+    assert pts.tolist() == [[2.0, 0.0]] and not deg
     away = np.array([[10.0, 25.4, 8.0, 0.0]])                           # same lane, already past x = 2
     assert orc.detect_collisions(ego, away).agent_collide == [False]
     parallel = np.array([[-2.0, 0.0, 8.0, np.pi / 2]])                  # opposite lane, never crosses within 3 s

@@ -147,6 +147,33 @@ def test_cuda_prepare_and_cost_against_reference():
     assert np.all(np.abs(tot - G["ss_f"]) <= 1e-5 * np.maximum(1.0, np.abs(G["ss_f"])))
     ref = G["ss_components"]
     assert np.all(np.abs(c6[:, :4] - ref[:, :4]) <= 1e-5 * np.maximum(1.0, np.abs(ref[:, :4])))
+    # A7: the archive file's obstacle-distance term (agents/archive/pure_mpc.py:189-196, BASELINE config 3) as evaluated by
+    # the archive file itself, and the collision term 3000 v^2 (agents/pure_mpc.py:179-183; dead code in the shipped file,
+    # `manual_collision_avoidance = True` at :82, so its number comes from the formula) -- both through a second handle
+    # with weight_distance = 10, weight_collision = 1.  Tolerance 5e-4 relative: the reference carries the other vehicles'
+    # in-NLP positions in float32 (quirk Q11), plus the conditioning of 1/d^2 near contact.
+    import helpers
+    arch = pkg.BatchedPureMPC(CFG, vehicles_count=V, max_batch=S, collision_check=True, weight_distance=10.0, weight_collision=1.0)
+    ws2 = arch.prepare_batch(torch.from_numpy(G["obs"]).cuda(), ref_speed=torch.from_numpy(rs).cuda())
+    _, c6b, totb = arch.rollout_cost(ws2, torch.from_numpy(G["ss_U"].astype(np.float32)).cuda())
+    c6b, totb = c6b.cpu().numpy().astype(np.float64), totb.cpu().numpy().astype(np.float64)
+    n_checked = 0
+    for i in range(S):
+        ag = orc.OraclePureMPCAgent(horizon=N, vehicles_count=V, collision_check=True, weight_distance=10.0, weight_collision=1.0)
+        parsed = orc.parse_obs(G["obs"][i], V)
+        ag.check_collision(parsed)
+        prob = ag.build_problem(parsed, ref_speed=np.array([[G["ref_speed"][i]]]) if G["has_ref_speed"][i] else None)
+        near, dist_tol = helpers.distance_conditioning(prob, G["ss_U"][i])
+        coll = 3000.0 * float(np.sum(G["ss_X"][i][:N, 3] ** 2)) if G["ss_is_collide"][i] else 0.0
+        assert abs(c6b[i, 5] - coll) <= 1e-5 * max(1.0, coll), i
+        if near:
+            continue
+        dref = G["ss_distance_component"][i]
+        assert abs(c6b[i, 4] - dref) <= 5e-4 * max(1.0, abs(dref)) + dist_tol, (i, c6b[i, 4], dref)
+        want = G["ss_f"][i] + 10.0 * dref + 1.0 * coll
+        assert abs(totb[i] - want) <= 1e-5 * max(1.0, abs(want)) + 10.0 * (5e-4 * max(1.0, abs(dref)) + dist_tol), i
+        n_checked += 1
+    assert n_checked >= 0.9 * S and float(np.mean(G["ss_is_collide"])) > 0.2
 
 
 @pytest.mark.gpu
