@@ -36,7 +36,8 @@ def mpcrl_controller(algo, deterministic: bool = False) -> Callable:
 
 @torch.no_grad()
 def evaluate(controller: Callable, env, n_episodes: int, max_steps: int = 150) -> Dict[str, float]:
-    """Runs until `n_episodes` episodes have finished (all environments in parallel, each restarting in place)."""
+    """Runs ceil(n_episodes / B) complete episodes in every environment (all in parallel, each restarting in place) and
+    aggregates them; `episodes` in the result is the number counted (a multiple of B, >= n_episodes)."""
     B, dev = env.B, env.device
     obs = env.reset()
     start = torch.ones(B, dtype=torch.bool, device=dev)
@@ -45,7 +46,12 @@ def evaluate(controller: Callable, env, n_episodes: int, max_steps: int = 150) -
     tot = {"episodes": 0, "successes": 0, "collisions": 0, "total_steps": 0.0, "total_speed": 0.0}
     dt = env.sub * env.dt_sim
     guard = 0
-    while tot["episodes"] < n_episodes:
+    # every environment contributes the same number of complete episodes (its first `quota`): counting the first
+    # n_episodes episodes to FINISH anywhere would over-sample short ones (early crashes) -- the reference runs n
+    # complete episodes one after another (main/model_comparison.py:40-105)
+    quota = -(-int(n_episodes) // B)
+    done_count = torch.zeros(B, dtype=torch.long, device=dev)
+    while int(done_count.min()) < quota:
         action = controller(obs, start)
         speed_sum += env.ego[:, 3]                          # speed before the step (main/model_comparison.py:62-63)
         obs, _, done, info = env.step(action)
@@ -55,19 +61,19 @@ def evaluate(controller: Callable, env, n_episodes: int, max_steps: int = 150) -
             obs = env.reset(over)
         fin = done | over
         if bool(fin.any()):
-            k = int(fin.sum())
-            take = min(k, n_episodes - tot["episodes"])
-            idx = torch.nonzero(fin).flatten()[:take]
-            tot["episodes"] += take
+            cnt = fin & (done_count < quota)
+            idx = torch.nonzero(cnt).flatten()
+            tot["episodes"] += int(idx.numel())
             tot["successes"] += int(info["arrived"][idx].sum())
             tot["collisions"] += int(info["crashed"][idx].sum())
             tot["total_steps"] += float(steps[idx].sum())
             tot["total_speed"] += float((speed_sum[idx] / steps[idx]).sum())
+            done_count += fin.long()
             steps[fin] = 0
             speed_sum[fin] = 0
         start = fin
         guard += 1
-        if guard > 100 * max_steps:
+        if guard > 100 * max_steps * quota:
             raise RuntimeError("evaluation did not finish: the environment never ends an episode")
     n = max(tot["episodes"], 1)
     return {"episodes": tot["episodes"], "success_rate": tot["successes"] / n, "collision_rate": tot["collisions"] / n,

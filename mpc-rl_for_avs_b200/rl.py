@@ -242,16 +242,25 @@ class ActorCritic(nn.Module):
         shape = (64, action_dim) if use_sde else (action_dim,)
         self.log_std = nn.Parameter(torch.full(shape, float(log_std_init)))
         self._theta = None                                    # [B, 64, A] exploration matrices (gSDE)
+        self._theta_pinned = False                            # a CUDA graph holds the buffer's address
 
     def value(self, obs):
         return self.value_net(self.mlp_extractor.value_net(obs)).squeeze(-1)
 
     def reset_noise(self, n_envs: int) -> None:
+        """Draws the exploration matrices of the ROLLOUT (one per environment).  The buffer is only ever updated in
+        place once it exists: a captured CUDA graph reads its address, so re-binding it (e.g. for a minibatch of a
+        different size) would leave the graph reading freed memory.  `evaluate_actions` never uses the matrices, so the
+        update loop has no reason to call this."""
         if self.use_sde:
             std = self.log_std.detach().exp()
             theta = torch.randn(n_envs, *std.shape, device=std.device) * std
-            if self._theta is not None and self._theta.shape == theta.shape and self._theta.device == theta.device:
+            if self._theta is None:
+                self._theta = theta
+            elif self._theta.shape == theta.shape and self._theta.device == theta.device:
                 self._theta.copy_(theta)                      # same storage: a captured CUDA graph keeps reading it
+            elif self._theta_pinned:
+                raise RuntimeError("reset_noise with a different shape after a CUDA graph captured the noise buffer")
             else:
                 self._theta = theta
 
@@ -375,6 +384,7 @@ class _MPCRollout:
         with torch.cuda.graph(g):
             self._transition()
         self._cuda_graph = g
+        self.policy._theta_pinned = True                    # the graph reads the noise buffer by address from now on
 
     def collect_rollouts(self):
         B, T, dev = self.env.B, self.n_steps, self.env.device
@@ -492,8 +502,6 @@ class PPOMPC(_MPCRollout):
             perm = torch.randperm(n, device=obs_f.device, generator=self.gen)
             for lo in range(0, n, bs):
                 idx = perm[lo:lo + bs]
-                if self.policy.use_sde:
-                    self.policy.reset_noise(idx.shape[0])
                 values, logp, entropy = self.policy.evaluate_actions(obs_f[idx], act_f[idx])
                 a = adv_f[idx]
                 if self.normalize_advantage and a.numel() > 1:
@@ -506,7 +514,10 @@ class PPOMPC(_MPCRollout):
                 loss = policy_loss + self.ent_coef * entropy_loss + self.vf_coef * value_loss
                 with torch.no_grad():
                     log_ratio = logp - logp_f[idx]
-                    approx_kl = float(((log_ratio.exp() - 1) - log_ratio).mean())
+                    kl_t = ((log_ratio.exp() - 1) - log_ratio).mean()
+                    if self.target_kl is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                        dist.all_reduce(kl_t, op=dist.ReduceOp.AVG)      # every rank must take the same branch below
+                    approx_kl = float(kl_t)
                     clip_frac = float(((ratio - 1).abs() > self.clip_range).float().mean())
                 if self.target_kl is not None and approx_kl > 1.5 * self.target_kl:
                     stop = True

@@ -130,7 +130,7 @@ def test_evaluation_harness_cpu():
     res = evaluation.compare({"pure_mpc": evaluation.pure_mpc_controller(stub),
                               "mpcrl": evaluation.mpcrl_controller(algo)}, make_env, n_episodes=40, max_steps=30)
     for r in res.values():
-        assert r["episodes"] == 40 and 0 <= r["success_rate"] <= 1 and 0 <= r["collision_rate"] <= 1
+        assert r["episodes"] == 48 and 0 <= r["success_rate"] <= 1 and 0 <= r["collision_rate"] <= 1   # ceil(40 / 16) = 3 complete episodes per environment
         assert 1 <= r["avg_steps"] <= 30 and abs(r["avg_time"] - r["avg_steps"] * 0.1) < 1e-6 and r["avg_speed"] > 0
     # same seeds -> same numbers
     again = evaluation.evaluate(evaluation.pure_mpc_controller(stub), make_env(), 40, 30)
@@ -183,9 +183,18 @@ def test_graph_captured_rollout_gpu():
     for Algo in (A2CMPC, PPOMPC):
         mpc = pkg.BatchedPureMPC(cfg, vehicles_count=10, max_batch=B, collision_check=True)
         algo = Algo(BatchedIntersectionEnv(B, 9, device="cuda", seed=9, duration_steps=20), mpc, n_steps=T, graph=True)
+        ptrs, thetas = [], []
         for _ in range(3):
             log = algo.train_step()
+            if algo.policy.use_sde:                      # gSDE (PPO default): the graph reads the noise buffer by address
+                ptrs.append(algo.policy._theta.data_ptr())
+                thetas.append(algo.policy._theta.clone())
         assert algo._cuda_graph is not None and all(np.isfinite(v) for v in log.values())
+        if algo.policy.use_sde:
+            assert len(set(ptrs)) == 1 and tuple(algo.policy._theta.shape) == (B, 64, 1)      # never re-bound by the update loop
+            assert not torch.equal(thetas[0], thetas[1]) and not torch.equal(thetas[1], thetas[2])   # resampled per rollout
+            with pytest.raises(RuntimeError):
+                algo.policy.reset_noise(B // 2)         # would re-bind storage a captured graph still reads
         assert int(algo._row) == T and algo.num_timesteps == 3 * B * T
         obs_buf, buf = algo._obs_buf, algo._buf
         assert (obs_buf[:, :, 0] == 1).all() and torch.isfinite(obs_buf).all()         # every row written (presence flag of the ego)
