@@ -270,19 +270,24 @@ def main() -> None:
         batches.append((obs.contiguous(), rsn))
     dev_batches = [(o.to(dev), r.to(dev)) for o, r in batches]
     host_batches = [(o.pin_memory(), r.pin_memory()) for o, r in batches]
-    gatherer = pkg.sharding.ActionGather(total, dev) if world > 1 else None
-    if gatherer is not None:
-        agent.bind_actions(gatherer.local)       # k_solve writes this rank's actions into its slice of the gathered buffer
+    # two gathered-action buffers used alternately: k_solve writes this rank's actions straight into its slice, and the
+    # in-place NCCL all-gather of step i runs on a side stream while k_prepare / k_solve of step i + 1 execute
+    pipe = pkg.sharding.PipelinedActionGather(total, dev) if world > 1 else None
+    gatherer = pipe.slots[0] if pipe is not None else None
 
     def step(i):
         o, r = dev_batches[i % n_unique]
         agent.reset()
+        if pipe is not None:
+            agent.bind_actions(pipe.acquire(i).local)
         a = agent.predict_batch(o, ref_speed=r)
-        if gatherer is not None:
-            gatherer.gather()                    # in-place NCCL all-gather: every rank ends up with all actions
+        if pipe is not None:
+            pipe.issue(i)                        # every rank ends up with all actions (pipe.result(i))
         return a
 
     def barrier():
+        if pipe is not None:
+            pipe.drain()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -301,6 +306,8 @@ def main() -> None:
     e0.record()
     for i in range(args.steps):
         step(args.warmup + i)
+    if pipe is not None:
+        pipe.drain()                             # the last all-gather belongs to the timed region
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -349,22 +356,23 @@ def main() -> None:
         B5 = (1 << 20) // world
         a5 = pkg.BatchedPureMPC(CFG, vehicles_count=M + 1, max_batch=B5, device=local, collision_check=True,
                                 weight_distance=W_DIST, n_starts=args.n_starts, **tune)
-        g5 = pkg.sharding.ActionGather(B5 * world, dev)
-        a5.bind_actions(g5.local)
+        g5 = pkg.sharding.PipelinedActionGather(B5 * world, dev)
         o5, rs5, has5 = pkg.make_scenarios(B5, M, seed=555 + rank)
         r5 = torch.where(has5.reshape(-1, 1), rs5, torch.full_like(rs5, float("nan"))).reshape(-1).contiguous().to(dev)
         o5 = o5.contiguous().to(dev)
 
         def s5(i):
             a5.reset()
+            a5.bind_actions(g5.acquire(i).local)
             a5.predict_batch(o5, ref_speed=r5)
-            g5.gather()
+            g5.issue(i)
         s5(0)
         barrier()
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         c0.record()
         for i in range(3):
             s5(i)
+        g5.drain()
         c1.record()
         barrier()
         t5 = torch.tensor([c0.elapsed_time(c1) / 3], device=dev)

@@ -77,3 +77,57 @@ class ActionGather:
             else:                                            # gloo (CPU tests): list form on views of the same buffer
                 dist.all_gather([self.buffer[r * self.n_max:(r + 1) * self.n_max] for r in range(self.world)], self._send.clone())
         return self.buffer[: self.total] if self._even else self.buffer.index_select(0, self._rows)
+
+
+class PipelinedActionGather:
+    """Takes the all-gather off the critical path: two `ActionGather` buffers used alternately.  The collective of step
+    i is issued on a side stream as soon as the solve of step i has been enqueued and runs while `k_prepare` / `k_solve`
+    of step i + 1 execute; the caller only waits for it when it needs the gathered actions (or the buffer again).
+
+        g = pipe.acquire(i)            # buffer of step i (waits for the gather of step i - 2 that used it)
+        agent.bind_actions(g.local)    # the solve kernel writes this rank's slice
+        agent.predict_batch(...)
+        pipe.issue(i)                  # all-gather of step i on the side stream
+        ...
+        full = pipe.result(i)          # [total, 2]; the current stream waits for that gather
+
+    On CPU tensors (gloo, tests) there are no streams: `issue` runs the collective synchronously."""
+
+    def __init__(self, total: int, device, dtype=torch.float32, depth: int = 2):
+        self.slots = [ActionGather(total, device, dtype) for _ in range(depth)]
+        self.device = torch.device(device)
+        self.cuda = self.device.type == "cuda"
+        self._full = [None] * depth
+        if self.cuda:
+            self.side = torch.cuda.Stream(device=self.device)
+            self._ready = [torch.cuda.Event() for _ in range(depth)]      # solve of the slot's step enqueued
+            self._done = [None] * depth                                   # gather of the slot's step finished
+
+    def acquire(self, i: int) -> ActionGather:
+        k = i % len(self.slots)
+        if self.cuda and self._done[k] is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._done[k])
+        return self.slots[k]
+
+    def issue(self, i: int) -> None:
+        k = i % len(self.slots)
+        if not self.cuda:
+            self._full[k] = self.slots[k].gather()
+            return
+        self._ready[k].record(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(self._ready[k])
+            self._full[k] = self.slots[k].gather()
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+            self._done[k] = ev
+
+    def result(self, i: int) -> torch.Tensor:
+        k = i % len(self.slots)
+        if self.cuda and self._done[k] is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._done[k])
+        return self._full[k]
+
+    def drain(self) -> None:
+        if self.cuda:
+            torch.cuda.current_stream(self.device).wait_stream(self.side)

@@ -38,6 +38,18 @@ def _worker(rank, world, port, total, q):
     for rep in range(2):                                  # the buffer is reused step after step
         g.local.copy_(local + rep)
         assert torch.equal(g.gather(), full + rep)
+    # pipelined form (two buffers, the gather of step i overlaps step i + 1 on a GPU; synchronous on CPU)
+    from mpc_rl_for_avs_b200.sharding import PipelinedActionGather
+    pipe = PipelinedActionGather(total, "cpu")
+    for step in range(5):
+        gg = pipe.acquire(step)
+        assert gg is pipe.slots[step % 2]
+        gg.local.copy_(local + 10 * step)
+        pipe.issue(step)
+        if step > 0:
+            assert torch.equal(pipe.result(step - 1), full + 10 * (step - 1))      # the previous step's result is still intact
+    pipe.drain()
+    assert torch.equal(pipe.result(4), full + 40)
     q.put((rank, full.numpy()))
     dist.barrier()
     dist.destroy_process_group()
