@@ -159,6 +159,22 @@ template <typename T> MPC_HD RefPoint<T> ref_point(const RefTab<T>& rt, const Pr
   return r;
 }
 
+// same, with the positions taken from the problem's own column where the slot file stages them (bit-identical values:
+// the column holds exactly T(xy - x0) of the rows j(k))
+template <typename T, typename SL>
+MPC_HD RefPoint<T> ref_point(const RefTab<T>& rt, const ProblemScalars<T>& p, const SL& sl, int k) {
+  if constexpr (SL::kRefStaged) {
+    int j = p.ego_index + k;
+    j = j < kNRef - 1 ? j : kNRef - 1;
+    RefPoint<T> r;
+    r.x = sl.R(k, 0); r.y = sl.R(k, 1);
+    r.h = rt.hsc[j * kRefStride]; r.sh = rt.hsc[j * kRefStride + 1]; r.ch = rt.hsc[j * kRefStride + 2];
+    return r;
+  } else {
+    return ref_point(rt, p, k);
+  }
+}
+
 template <typename T> MPC_HD T ref_speed_at(const ProblemScalars<T>& p, int k) {
   return (k < p.vr_n) ? p.vr_a + T(k) * p.vr_slope : p.vr_b;
 }
@@ -198,6 +214,7 @@ template <typename T, bool kPack, int kStride = 0> struct Slots {
   int N, M;
   MPC_HD T& at(int s) const { return base[(unsigned)s * (unsigned)(kStride > 0 ? kStride : stride)]; }
   static constexpr int kGainWords = kPack ? 7 : 14;
+  static constexpr bool kRefStaged = false;      // path positions are read from the block's table at every use
   // layout
   MPC_HD int oU() const { return 0; }                       // 2N
   MPC_HD int oX() const { return 2 * N; }                   // 4(N+1)
@@ -256,10 +273,16 @@ template <int kStride> struct SlotsTmem {
   uint32_t taddr;        // (lane quarter << 16) | first column of this warp's range
   int N, M;
   static constexpr bool kTmem = true;
+  // the ego-relative path positions of the problem's N stages live in its own column (written once when the problem is
+  // loaded): the per-lane table reads at divergent rows ego_index + k -- an FP64 pair per stage in every sweep -- were a
+  // quarter of the kernel's shared-memory wavefronts (bank conflicts, profiles/r01_k_solve_ncu_full.json)
+  static constexpr bool kRefStaged = true;
   __device__ __forceinline__ float& at(int s) const { return base[(unsigned)s * (unsigned)kStride]; }
   __device__ __forceinline__ int oU() const { return 0; }
   __device__ __forceinline__ int oX() const { return 2 * N; }
   __device__ __forceinline__ int oO() const { return 2 * N + 4 * (N + 1); }
+  __device__ __forceinline__ int oR() const { return 2 * N + 4 * (N + 1) + 4 * M; }
+  __device__ __forceinline__ float& R(int k, int i) const { return at(oR() + 2 * k + i); }
   __device__ __forceinline__ float& U(int k, int i) const { return at(oU() + 2 * k + i); }
   __device__ __forceinline__ float& X(int k, int i) const { return at(oX() + 4 * k + i); }
   __device__ __forceinline__ float& O(int m, int i) const { return at(oO() + 4 * m + i); }
@@ -289,7 +312,7 @@ template <int kStride> struct SlotsTmem {
     asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
   }
 };
-MPC_HD int slots_per_problem_tmem(int N, int M) { return 2 * N + 4 * (N + 1) + 4 * M; }
+MPC_HD int slots_per_problem_tmem(int N, int M) { return 2 * N + 4 * (N + 1) + 4 * M + 2 * N; }
 #endif
 
 MPC_HD int slots_per_problem(int N, int M, bool pack) { return 2 * N + 4 * (N + 1) + (pack ? 7 : 14) * N + 4 * M; }
@@ -333,7 +356,7 @@ MPC_HD void euler_step(T& x, T& y, T& th, T& v, T a, const Steer<T>& st, T dt, T
 template <typename T, typename SL>
 MPC_HD T stage_cost(const SolverConfig& cfg, const ProblemScalars<T>& p, const RefTab<T>& ref,
                     const SL& sl, int k, T x, T y, T th, T v, T a, T d, T ap, T dp, T* comp) {
-  const RefPoint<T> r = ref_point(ref, p, k);
+  const RefPoint<T> r = ref_point(ref, p, sl, k);
   T dx = x - r.x, dy = y - r.y;
   T perp = dx * r.sh - dy * r.ch;
   T para = dx * r.ch + dy * r.sh;
@@ -519,7 +542,7 @@ MPC_HD void backward_pass(const SolverConfig& cfg, const ProblemScalars<T>& p, c
     T lx = T(0), ly = T(0), lth = T(0), lv = T(0);
     T lxx = T(0), lxy = T(0), lyy = T(0), lthth = T(0), lvv = T(0);
     if (!cfg.literal_no_collision) {
-      const RefPoint<T> r = ref_point(ref, p, k);
+      const RefPoint<T> r = ref_point(ref, p, sl, k);
       const T sh = r.sh, ch = r.ch;
       T dx = x - r.x, dy = y - r.y;
       T perp = dx * sh - dy * ch, para = dx * ch + dy * sh;

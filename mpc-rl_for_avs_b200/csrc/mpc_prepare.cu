@@ -374,10 +374,16 @@ k_prepare(const PrepareParams P) {
     is_col = 0;
   }
 
-  if (!live) return;
-
-  // ---- per-vehicle outputs ---------------------------------------------------------------------
-  if (l < P.M) {
+  // ---- outputs.  The SoA planes are strided by the batch, so a group writing its own environment's element would touch
+  // 4 (16) bytes per plane per warp: the values of the block's PPB environments are staged in shared memory and each
+  // plane is then written as one run of PPB consecutive elements (full 32-byte sectors).
+  constexpr int kFloatRows = 10, kIntRows = 6;          // s0 x4, w x3, vr_a, vr_slope, vr_b | ego_index, vr_n, n_obs, mem, memo, stop
+  __shared__ float s_oobs[MPC_MAX_OBSTACLES * 4][PPB];
+  __shared__ float s_of[kFloatRows][PPB];
+  __shared__ int s_oi[kIntRows][PPB];
+  __shared__ uint8_t s_ou[2][PPB];                      // is_collide, degenerate
+  // ---- per-vehicle outputs ([B][M] layouts: a warp already writes consecutive elements) -------------
+  if (live && l < P.M) {
     if (P.col.agent_collide) P.col.agent_collide[(size_t)b * P.M + l] = (uint8_t)((P.collision_check && !latched && !aborted) ? my_flag : 0);
     if (P.col.conflict_index) P.col.conflict_index[(size_t)b * P.M + l] = (P.collision_check && !latched && !aborted && my_flag) ? my_cidx : -1;
     if (P.col.conflict_point) {
@@ -385,65 +391,84 @@ k_prepare(const PrepareParams P) {
       P.col.conflict_point[((size_t)b * P.M + l) * 2] = hit ? (float)my_qx : nanf("");
       P.col.conflict_point[((size_t)b * P.M + l) * 2 + 1] = hit ? (float)my_qy : nanf("");
     }
-    float* O = P.ws.obstacles;
-    const size_t B = P.B;
-    O[((size_t)l * 4 + 0) * B + b] = has_veh ? (float)ox : 0.f;
-    O[((size_t)l * 4 + 1) * B + b] = has_veh ? (float)oy : 0.f;
-    O[((size_t)l * 4 + 2) * B + b] = has_veh ? (float)incx : 0.f;
-    O[((size_t)l * 4 + 3) * B + b] = has_veh ? (float)incy : 0.f;
+  }
+  if (l < P.M) {
+    s_oobs[l * 4 + 0][g] = has_veh ? (float)ox : 0.f;
+    s_oobs[l * 4 + 1][g] = has_veh ? (float)oy : 0.f;
+    s_oobs[l * 4 + 2][g] = has_veh ? (float)incx : 0.f;
+    s_oobs[l * 4 + 3][g] = has_veh ? (float)incy : 0.f;
   }
   if (LPP < MPC_MAX_OBSTACLES && l == 0) {
-    for (int m = LPP; m < P.M; ++m) {                   // more vehicles than lanes: not reachable with LPP >= M
-      for (int c = 0; c < 4; ++c) P.ws.obstacles[((size_t)m * 4 + c) * P.B + b] = 0.f;
+    for (int m = LPP; m < P.M; ++m)                     // more vehicles than lanes: not reachable with LPP >= M
+      for (int c = 0; c < 4; ++c) s_oobs[m * 4 + c][g] = 0.f;
+  }
+  if (l == 0) {
+    // ---- weights, reference-speed profile (update_reference_states, pure_mpc.py:678-724) -----------
+    float w_s = P.w_speed, w_c = P.w_control, w_d = P.w_diff;
+    if (P.weights) { w_s = P.weights[(size_t)bb * 3]; w_c = P.weights[(size_t)bb * 3 + 1]; w_d = P.weights[(size_t)bb * 3 + 2]; }
+    if (is_col) w_s = 100.f;                              // pure_mpc.py:143-147
+    float vr_a = 0.f, vr_slope = 0.f, vr_b = (float)s_ref[0][2];
+    int vr_n = 0;
+    bool override_v = false;
+    if (P.ref_speed) {
+      const float rs = P.ref_speed[bb];
+      if (rs == rs) { override_v = true; vr_b = fminf(fmaxf(rs, 0.f), 30.f); }   // np.clip(., 0, 30), takes precedence
+    }
+    if (!override_v && is_col && cmin >= 0) {
+      int stop = cmin - kSafetyBuffer;
+      stop = stop > ego_index + 1 ? stop : ego_index + 1;
+      stop = stop < kNRef - 1 ? stop : kNRef - 1;
+      const int n = stop - ego_index;
+      if (n > 0) {
+        vr_n = n; vr_a = (float)ev; vr_b = 0.f;
+        vr_slope = n > 1 ? (float)(-ev / (double)(n - 1)) : 0.f;   // np.linspace(v, 0, n)
+        stop_index = stop;
+      }
+    }
+    s_of[0][g] = (float)ex; s_of[1][g] = (float)ey; s_of[2][g] = (float)eth; s_of[3][g] = (float)ev;
+    s_of[4][g] = w_s; s_of[5][g] = w_c; s_of[6][g] = w_d;
+    s_of[7][g] = vr_a; s_of[8][g] = vr_slope; s_of[9][g] = vr_b;
+    s_oi[0][g] = ego_index; s_oi[1][g] = vr_n; s_oi[2][g] = n_obs; s_oi[3][g] = mem; s_oi[4][g] = memo; s_oi[5][g] = stop_index;
+    s_ou[0][g] = (uint8_t)is_col; s_ou[1][g] = (uint8_t)any_deg;
+  }
+  __syncthreads();
+  const int nb = P.count - (int)blockIdx.x * PPB < PPB ? P.count - (int)blockIdx.x * PPB : PPB;   // live environments of this block
+  const size_t b0 = (size_t)P.first + (size_t)blockIdx.x * PPB;
+  const size_t SB = (size_t)P.B;
+  for (int q = threadIdx.x; q < P.M * 4 * PPB; q += blockDim.x) {
+    const int plane = q / PPB, e = q % PPB;
+    if (e < nb) P.ws.obstacles[(size_t)plane * SB + b0 + e] = s_oobs[plane][e];
+  }
+  for (int q = threadIdx.x; q < kFloatRows * PPB; q += blockDim.x) {
+    const int row = q / PPB, e = q % PPB;
+    if (e >= nb) continue;
+    const float v = s_of[row][e];
+    float* dst = row < 4 ? P.ws.s0 + (size_t)row * SB : row == 4 ? P.ws.w_speed : row == 5 ? P.ws.w_control : row == 6 ? P.ws.w_diff
+               : row == 7 ? P.ws.vr_a : row == 8 ? P.ws.vr_slope : P.ws.vr_b;
+    dst[b0 + e] = v;
+  }
+  for (int q = threadIdx.x; q < kIntRows * PPB; q += blockDim.x) {
+    const int row = q / PPB, e = q % PPB;
+    if (e >= nb) continue;
+    const int v = s_oi[row][e];
+    int32_t* dst = row == 0 ? P.ws.ego_index : row == 1 ? P.ws.vr_n : row == 2 ? P.ws.n_obs
+                 : row == 3 ? (P.collision_check ? P.latch.collision_memory : nullptr) : row == 4 ? (P.collision_check ? P.latch.memo_conflict : nullptr)
+                 : P.col.stop_index;
+    if (dst) dst[b0 + e] = v;
+    if (row == 0 && P.col.ego_index) P.col.ego_index[b0 + e] = v;
+  }
+  for (int q = threadIdx.x; q < 2 * PPB; q += blockDim.x) {
+    const int row = q / PPB, e = q % PPB;
+    if (e >= nb) continue;
+    const uint8_t v = s_ou[row][e];
+    if (row == 0) {
+      P.ws.is_collide[b0 + e] = v;
+      if (P.collision_check) P.latch.is_collide[b0 + e] = v;
+      if (P.col.is_collide) P.col.is_collide[b0 + e] = v;
+    } else if (P.col.degenerate) {
+      P.col.degenerate[b0 + e] = v;
     }
   }
-
-  if (l != 0) return;
-  // ---- weights, reference-speed profile (update_reference_states, pure_mpc.py:678-724) -----------
-  float w_s = P.w_speed, w_c = P.w_control, w_d = P.w_diff;
-  if (P.weights) { w_s = P.weights[(size_t)b * 3]; w_c = P.weights[(size_t)b * 3 + 1]; w_d = P.weights[(size_t)b * 3 + 2]; }
-  if (is_col) w_s = 100.f;                              // pure_mpc.py:143-147
-  float vr_a = 0.f, vr_slope = 0.f, vr_b = (float)s_ref[0][2];
-  int vr_n = 0;
-  bool override_v = false;
-  if (P.ref_speed) {
-    const float rs = P.ref_speed[b];
-    if (rs == rs) { override_v = true; vr_b = fminf(fmaxf(rs, 0.f), 30.f); }   // np.clip(., 0, 30), takes precedence
-  }
-  if (!override_v && is_col && cmin >= 0) {
-    int stop = cmin - kSafetyBuffer;
-    stop = stop > ego_index + 1 ? stop : ego_index + 1;
-    stop = stop < kNRef - 1 ? stop : kNRef - 1;
-    const int n = stop - ego_index;
-    if (n > 0) {
-      vr_n = n; vr_a = (float)ev; vr_b = 0.f;
-      vr_slope = n > 1 ? (float)(-ev / (double)(n - 1)) : 0.f;   // np.linspace(v, 0, n)
-      stop_index = stop;
-    }
-  }
-  P.ws.s0[0 * (size_t)P.B + b] = (float)ex;
-  P.ws.s0[1 * (size_t)P.B + b] = (float)ey;
-  P.ws.s0[2 * (size_t)P.B + b] = (float)eth;
-  P.ws.s0[3 * (size_t)P.B + b] = (float)ev;
-  P.ws.ego_index[b] = ego_index;
-  P.ws.w_speed[b] = w_s;
-  P.ws.w_control[b] = w_c;
-  P.ws.w_diff[b] = w_d;
-  P.ws.vr_a[b] = vr_a;
-  P.ws.vr_slope[b] = vr_slope;
-  P.ws.vr_b[b] = vr_b;
-  P.ws.vr_n[b] = vr_n;
-  P.ws.is_collide[b] = (uint8_t)is_col;
-  P.ws.n_obs[b] = n_obs;
-  if (P.collision_check) {
-    P.latch.collision_memory[b] = mem;
-    P.latch.memo_conflict[b] = memo;
-    P.latch.is_collide[b] = (uint8_t)is_col;
-  }
-  if (P.col.is_collide) P.col.is_collide[b] = (uint8_t)is_col;
-  if (P.col.ego_index) P.col.ego_index[b] = ego_index;
-  if (P.col.stop_index) P.col.stop_index[b] = stop_index;
-  if (P.col.degenerate) P.col.degenerate[b] = (uint8_t)any_deg;
 }
 
 cudaError_t launch_prepare(const PrepareParams& p, cudaStream_t stream) {

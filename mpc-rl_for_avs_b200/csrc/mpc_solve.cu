@@ -63,7 +63,7 @@ __device__ __forceinline__ RefTab<float> stage_tables(float* smem) {
 
 template <typename SL>
 __device__ __forceinline__ void load_problem(const MpcProblemBatch& b, int B, int i, const SolverConfig& cfg,
-                                             ProblemScalars<float>& p, const SL& sl) {
+                                             ProblemScalars<float>& p, const SL& sl, const RefTab<float>& ref) {
   p.ego_index = b.ego_index[i];
   int n = b.n_obs ? b.n_obs[i] : 0;
   p.n_obs = n < cfg.M ? n : cfg.M;
@@ -91,15 +91,24 @@ __device__ __forceinline__ void load_problem(const MpcProblemBatch& b, int B, in
       sl.O(m, 0) = 0.f; sl.O(m, 1) = 0.f; sl.O(m, 2) = 0.f; sl.O(m, 3) = 0.f;
     }
   }
+  if constexpr (SL::kRefStaged) {
+#pragma unroll 1
+    for (int k = 0; k < cfg.N; ++k) {
+      int j = p.ego_index + k;
+      j = j < kNRef - 1 ? j : kNRef - 1;
+      sl.R(k, 0) = (float)(ref.xy[2 * j] - p.x0);
+      sl.R(k, 1) = (float)(ref.xy[2 * j + 1] - p.y0);
+    }
+  }
 }
 
 // work item -> (problem, start); first controls of a fresh item (cold start pure_mpc.py:244, a portfolio start, or the
 // opt-in warm start for start 0)
 template <typename SL>
 __device__ __forceinline__ void begin_item(const SolverConfig& cfg, const MpcProblemBatch& batch, int B, int idx, const float* __restrict__ u_init,
-                                           ProblemScalars<float>& p, const SL& sl, SolveState<float>& s) {
+                                           ProblemScalars<float>& p, const SL& sl, SolveState<float>& s, const RefTab<float>& ref) {
   const int st = idx / B, pb = idx - st * B;
-  load_problem(batch, B, pb, cfg, p, sl);
+  load_problem(batch, B, pb, cfg, p, sl, ref);
   solve_init(cfg, sl, s);
   if (st > 0) {
     apply_start<float>(cfg, sl, st);
@@ -169,7 +178,7 @@ k_solve(const SolverConfig cfg, const MpcProblemBatch batch, const MpcSolveOut o
       idx = atomicAdd(work_counter, 1);
       active = idx < B * n_starts;
       if (active) {
-        begin_item(cfg, batch, B, idx, u_init, p, sl, s);
+        begin_item(cfg, batch, B, idx, u_init, p, sl, s, ref);
         fresh = true;
       }
     }
@@ -284,7 +293,7 @@ k_solve_tmem(const SolverConfig cfg, const MpcProblemBatch batch, const MpcSolve
       first_wave = false;
       active = idx < B * n_starts;
       if (active) {
-        begin_item(cfg, batch, B, idx, u_init, p, sl, s);
+        begin_item(cfg, batch, B, idx, u_init, p, sl, s, ref);
         fresh = true;
       } else {
         saw_empty = true;
@@ -523,7 +532,7 @@ k_rollout_cost(const SolverConfig cfg, const MpcProblemBatch batch, const int B,
   const Slots<float, true> sl{smem + kTabFloats + threadIdx.x, (int)blockDim.x, cfg.N, cfg.M};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) {
     ProblemScalars<float> p;
-    load_problem(batch, B, i, cfg, p, sl);
+    load_problem(batch, B, i, cfg, p, sl, ref);
     for (int k = 0; k < cfg.N; ++k) {
       sl.U(k, 0) = U[((size_t)i * cfg.N + k) * 2];
       sl.U(k, 1) = U[((size_t)i * cfg.N + k) * 2 + 1];

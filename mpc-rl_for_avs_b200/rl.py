@@ -532,3 +532,73 @@ class PPOMPC(_MPCRollout):
         self.stats["update_s"] += time.perf_counter() - t0
         last.update({"mean_reward": float(buf["rew"].mean()), "done_rate": float(buf["done"].mean())})
         return last
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Reference-signature wrappers: `A2C_MPC` / `PPO_MPC` with the constructor keywords and the `learn` /
+# `collect_rollouts` / `train` / `predict` method names of agents/a2c_mpc.py:53-244 and agents/ppo_mpc.py:94-483,
+# accepting n_envs > 1 (the reference is hard-wired to `self.env.envs[0]`, a2c_mpc.py:104 / ppo_mpc.py:198).
+# stable-baselines3 is not installable here, so these are NOT SB3 subclasses: `policy` must be "MlpPolicy" (the
+# 64-64 tanh actor-critic the reference builds, trainers/trainer_utils.py:6-44), `env` a BatchedIntersectionEnv, and
+# SB3-only arguments (tensorboard_log, policy_kwargs, rollout_buffer_class, callbacks ...) are accepted and ignored.
+# ---------------------------------------------------------------------------------------------------------------
+def _make_batched_mpc(env, pure_mpc_cfg, collision_check=True):
+    from .agent import BatchedPureMPC
+    return BatchedPureMPC(pure_mpc_cfg, vehicles_count=env.V, max_batch=env.B, device=env.device,
+                          collision_check=collision_check)
+
+
+class _SB3Surface:
+    def learn(self, total_timesteps: int, callback=None, log_interval: int = 100, tb_log_name: str = "", reset_num_timesteps: bool = True,
+              progress_bar: bool = False):
+        """OnPolicyAlgorithm.learn: alternate collect_rollouts / train until `total_timesteps` env steps were taken."""
+        start = 0 if reset_num_timesteps else self.num_timesteps
+        if reset_num_timesteps:
+            self.num_timesteps = 0
+        while self.num_timesteps - start < total_timesteps:
+            self.last_log = self.train_step()
+        return self
+
+    def train(self):
+        """SB3 splits collect_rollouts() and train(); the batched loop fuses them in train_step()."""
+        self.last_log = self.train_step()
+
+
+class A2C_MPC(_SB3Surface, A2CMPC):
+    """agents/a2c_mpc.py:53-109 keyword surface over the batched A2C-MPC loop."""
+
+    def __init__(self, mpcrl_cfg: Dict, version: str, pure_mpc_cfg: Dict, policy="MlpPolicy", env=None, learning_rate: float = 7e-4,
+                 n_steps: int = 64, gamma: float = 0.99, gae_lambda: float = 1.0, ent_coef: float = 0.0, vf_coef: float = 0.5,
+                 max_grad_norm: float = 0.5, rms_prop_eps: float = 1e-5, use_rms_prop: bool = True, use_sde: bool = False,
+                 sde_sample_freq: int = -1, normalize_advantage: bool = False, tensorboard_log=None, policy_kwargs=None,
+                 verbose: int = 0, seed: Optional[int] = None, device="auto", _init_setup_model: bool = True, graph: bool = False):
+        if policy not in ("MlpPolicy", None) or not use_rms_prop or sde_sample_freq != -1 or normalize_advantage:
+            raise NotImplementedError("only the reference's own settings: MlpPolicy, RMSprop, sde_sample_freq -1, normalize_advantage False")
+        self.mpcrl_cfg, self.normalize_advantage = mpcrl_cfg, normalize_advantage
+        self.mpc_agent = _make_batched_mpc(env, pure_mpc_cfg)
+        A2CMPC.__init__(self, env, self.mpc_agent, n_steps=n_steps, lr=learning_rate, gamma=gamma, gae_lambda=gae_lambda,
+                        ent_coef=ent_coef, vf_coef=vf_coef, max_grad_norm=max_grad_norm, rms_prop_eps=rms_prop_eps,
+                        seed=0 if seed is None else seed, version=version,
+                        action_dim=(mpcrl_cfg or {}).get("action_space_dim"), use_sde=use_sde, graph=graph)
+
+
+class PPO_MPC(_SB3Surface, PPOMPC):
+    """agents/ppo_mpc.py:94-200 keyword surface over the batched PPO-MPC loop (`use_collision_avoidance=False` selects
+    the pure_mpc_no_collision flow, ppo_mpc.py:186-199)."""
+
+    def __init__(self, mpcrl_cfg: Dict, version: str, pure_mpc_cfg: Dict, policy="MlpPolicy", env=None, use_collision_avoidance: bool = True,
+                 learning_rate: float = 3e-4, n_steps: int = 2048, batch_size: int = 64, n_epochs: int = 10, gamma: float = 0.99,
+                 gae_lambda: float = 0.95, clip_range: float = 0.2, clip_range_vf=None, normalize_advantage: bool = True,
+                 ent_coef: float = 0.0, vf_coef: float = 0.5, max_grad_norm: float = 0.5, use_sde: bool = True, sde_sample_freq: int = -1,
+                 rollout_buffer_class=None, rollout_buffer_kwargs=None, target_kl: Optional[float] = None, stats_window_size: int = 100,
+                 tensorboard_log=None, policy_kwargs=None, verbose: int = 0, seed: Optional[int] = None, device="auto",
+                 _init_setup_model: bool = True, graph: bool = False):
+        if policy not in ("MlpPolicy", None) or sde_sample_freq != -1:
+            raise NotImplementedError("only the reference's own settings: MlpPolicy, sde_sample_freq -1")
+        self.mpcrl_cfg = mpcrl_cfg
+        self.mpc_agent = _make_batched_mpc(env, pure_mpc_cfg, collision_check=use_collision_avoidance)
+        PPOMPC.__init__(self, env, self.mpc_agent, n_steps=n_steps, batch_size=batch_size, n_epochs=n_epochs, lr=learning_rate,
+                        gamma=gamma, gae_lambda=gae_lambda, clip_range=clip_range, clip_range_vf=clip_range_vf,
+                        normalize_advantage=normalize_advantage, ent_coef=ent_coef, vf_coef=vf_coef, max_grad_norm=max_grad_norm,
+                        target_kl=target_kl, use_sde=use_sde, seed=0 if seed is None else seed, version=version,
+                        action_dim=(mpcrl_cfg or {}).get("action_space_dim"), graph=graph)
