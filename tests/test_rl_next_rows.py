@@ -238,3 +238,22 @@ def test_fused_env_step_matches_the_tensor_program_gpu():
         assert torch.equal(a._ctr, b._ctr) and torch.equal(a.t[same], b.t[same])
         n_done += int(da.sum()); n_crash += int(ia["crashed"].sum()); n_arrive += int(ia["arrived"].sum())
     assert n_done > B and n_crash > 0 and n_arrive > 0          # resets, crashes and arrivals were all exercised
+
+
+@pytest.mark.gpu
+def test_reference_signature_wrappers_gpu():
+    """`A2C_MPC` / `PPO_MPC` with the reference's constructor keywords (agents/a2c_mpc.py:53-109, agents/ppo_mpc.py:94-200)
+    and method names, n_envs > 1."""
+    from mpc_rl_for_avs_b200.rl import A2C_MPC, PPO_MPC, BatchedIntersectionEnv
+    B = 128
+    pure_mpc_cfg = {"horizon": 16, "render": False, "weight_speed": 1, "weight_control": 1, "weight_input_diff": 1, "speed_override": 0}
+    a2c = A2C_MPC(mpcrl_cfg={"action_space_dim": 1}, version="v0", pure_mpc_cfg=pure_mpc_cfg, policy="MlpPolicy",
+                  env=BatchedIntersectionEnv(B, 9, device="cuda", seed=3), learning_rate=7e-4, n_steps=4, gae_lambda=1.0, verbose=0)
+    a2c.learn(total_timesteps=2 * B * 4)
+    assert a2c.num_timesteps == 2 * B * 4 and a2c.mpc_agent.n_obstacles == 9 and np.isfinite(a2c.last_log["loss"])
+    ppo = PPO_MPC(mpcrl_cfg={"action_space_dim": 3}, version="v1", pure_mpc_cfg=pure_mpc_cfg, policy="MlpPolicy",
+                  env=BatchedIntersectionEnv(B, 9, device="cuda", seed=4), use_collision_avoidance=False, n_steps=4, batch_size=64, n_epochs=2)
+    ppo.train()
+    assert ppo.num_timesteps == B * 4 and not ppo.mpc_agent.collision_check and np.isfinite(ppo.last_log["loss"])
+    with pytest.raises(NotImplementedError):
+        A2C_MPC({}, "v0", pure_mpc_cfg, "CnnPolicy", BatchedIntersectionEnv(B, 9, device="cuda", seed=3))
