@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--n-steps", type=int, default=64)
     ap.add_argument("--horizon", type=int, default=16)         # config/cfg.yaml:90
     ap.add_argument("--warm-start", action="store_true")
+    ap.add_argument("--n-starts", type=int, default=1, help="MPC start portfolio (1 = the reference's single cold start; 0 = library default, 4)")
     ap.add_argument("--algo", choices=("a2c", "ppo"), default="a2c")
     ap.add_argument("--save", default="", help="write the policy as an SB3-layout zip")
     ap.add_argument("--eager", action="store_true", help="no CUDA graph: per-phase shares are measured instead")
@@ -40,7 +41,7 @@ def main():
     n_others = 9                                               # vehicles_count 10, config/cfg.yaml:2
     env = BatchedIntersectionEnv(args.envs, n_others, device=f"cuda:{local}", seed=1234 + rank)
     cfg = {"horizon": args.horizon, "weight_speed": 1, "weight_control": 1, "weight_input_diff": 1}
-    mpc = pkg.BatchedPureMPC(cfg, vehicles_count=n_others + 1, max_batch=args.envs, device=local, collision_check=True)
+    mpc = pkg.BatchedPureMPC(cfg, vehicles_count=n_others + 1, max_batch=args.envs, device=local, collision_check=True, n_starts=args.n_starts)
     Algo = A2CMPC if args.algo == "a2c" else PPOMPC
     algo = Algo(env, mpc, n_steps=args.n_steps, graph=not args.eager)
     algo.train_step()                                          # warm-up (allocator, first launches)
