@@ -37,6 +37,9 @@
 #ifndef MPC_OBS_UNROLL
 #define MPC_OBS_UNROLL 4
 #endif
+#ifndef MPC_LOOKAHEAD
+#define MPC_LOOKAHEAD 1         // look-ahead bound in the backward sweep (see backward_pass)
+#endif
 #define MPC_STR2(x) #x
 #define MPC_STR(x) MPC_STR2(x)
 #define MPC_PRAGMA_UNROLL_OBS _Pragma(MPC_STR(unroll MPC_OBS_UNROLL))
@@ -525,6 +528,19 @@ MPC_HD void backward_pass(const SolverConfig& cfg, const ProblemScalars<T>& p, c
   for (int i = 0; i < 6; ++i) pv[i] = T(0);
   T d1 = T(0), d2 = T(0);
   const T cc2 = T(0.02) * p.w_control;
+#if MPC_LOOKAHEAD
+  // Look-ahead bound (round 2).  When the steering of stage k+1 is pinned on its CONSTANT limit, stage k+1 cannot
+  // absorb a perturbation of its own state any more, so the bound of node k+2,
+  //   theta_{k+2} = theta_{k+1} + dt (v_{k+1} / L) sin beta(-+pi/3)  within [-pi, pi],
+  // is a linear inequality  la_cth dtheta_{k+1} + la_cv dv_{k+1} >= la_r  on the state that stage k produces -- a
+  // half-plane for du_k.  Without it the model of stage k happily steps across that line, the forward pass then lifts
+  // delta_{k+1} off its limit to stay feasible (a different smooth piece), the step is rejected, and the iteration creeps
+  // onto the kink instead of moving ALONG it (status "settled on a kink").  la_jump = the first-order price of lifting
+  // delta_{k+1} per radian of violation: if the multiplier of the half-plane exceeds it, crossing the line is worth it
+  // and the constraint is dropped for this sweep.
+  bool la_on = false;
+  T la_cth = T(0), la_cv = T(0), la_r = T(0), la_jump = T(0);
+#endif
   for (int k = N - 1; k >= 0; --k) {
     const T x = sl.X(k, 0), y = sl.X(k, 1), th = sl.X(k, 2), v = sl.X(k, 3);
     const T a = sl.U(k, 0), d = sl.U(k, 1);
@@ -741,6 +757,98 @@ MPC_PRAGMA_UNROLL_OBS
 #pragma unroll
       for (int jc = 0; jc < 6; ++jc) Kg[1][jc] = -(Rz[1][jc] + E01 * Kg[0][jc]) * ih;
     }
+#if MPC_LOOKAHEAD
+    {
+      bool la_next = false;
+      T nx_cth = T(0), nx_cv = T(0), nx_r = T(0), nx_jump = T(0);
+      const T lo0 = bx.lo_a - a, hi0 = bx.hi_a - a;
+      bool la_carry = false;                                  // this stage could not absorb the bound: hand it further back
+      if (la_on) {
+        const T n0 = la_cv * dt, n1 = la_cth * b3;            // B' c
+        const T nn = n0 * n0 + n1 * n1;
+        if (nn > T(1e-20) && n0 * k0 + n1 * k1 < la_r) {
+          la_carry = true;
+          // minimiser of the stage model on the line n'du = la_r inside the control box
+          const T inn = rcp_(nn);
+          const T p0 = la_r * n0 * inn, p1 = la_r * n1 * inn, t0_ = -n1, t1_ = n0;
+          const T Ht0 = h00 * t0_ + h01 * t1_, Ht1 = h01 * t0_ + h11 * t1_;
+          const T tHt = t0_ * Ht0 + t1_ * Ht1;
+          T tlo = T(-1e30), thi = T(1e30);
+          bool feas = tHt > T(0);
+          if (abs_(t0_) > T(1e-12)) { T u = (lo0 - p0) / t0_, w = (hi0 - p0) / t0_; tlo = max_(tlo, min_(u, w)); thi = min_(thi, max_(u, w)); }
+          else feas = feas && p0 >= lo0 - T(1e-6) && p0 <= hi0 + T(1e-6);
+          if (abs_(t1_) > T(1e-12)) { T u = (lo_dd - p1) / t1_, w = (hi_dd - p1) / t1_; tlo = max_(tlo, min_(u, w)); thi = min_(thi, max_(u, w)); }
+          else feas = feas && p1 >= lo_dd - T(1e-6) && p1 <= hi_dd + T(1e-6);
+          if (feas && tlo <= thi) {
+            const T tau = -((Ht0 * p0 + Ht1 * p1) + Qu[0] * t0_ + Qu[1] * t1_) / tHt;
+            const T tc = clamp_(tau, tlo, thi);
+            const T c0 = p0 + tc * t0_, c1 = p1 + tc * t1_;
+            const T lam = (n0 * (h00 * c0 + h01 * c1 + Qu[0]) + n1 * (h01 * c0 + h11 * c1 + Qu[1])) * inn;
+            la_carry = false;
+            if (lam <= la_jump) {
+              k0 = clamp_(c0, lo0, hi0); k1 = clamp_(c1, lo_dd, hi_dd);
+              // the policy keeps the line under a perturbation of this stage's state: n'du = la_r - m'dz, m = A'c
+              const T m2 = la_cth, m3 = la_cth * a34 + la_cv;
+              E00 = f00; E01 = f01; E11 = f11;
+              if (tc == tau) {                                // free along the line
+                const T tHn = (Ht0 * n0 + Ht1 * n1) * inn, itHt = rcp_(tHt);
+#pragma unroll
+                for (int jc = 0; jc < 6; ++jc) {
+                  const T mj = jc == 2 ? m2 : (jc == 3 ? m3 : T(0));
+                  const T along = (tHn * mj - (t0_ * Rz[0][jc] + t1_ * Rz[1][jc])) * itHt;
+                  Kg[0][jc] = -n0 * inn * mj + t0_ * along;
+                  Kg[1][jc] = -n1 * inn * mj + t1_ * along;
+                }
+                s0 = 0; s1 = 0;
+              } else {                                        // corner of the line and the box: nothing left to choose
+                const bool pin0 = (k0 <= lo0 || k0 >= hi0);   // which coordinate sits on the box
+#pragma unroll
+                for (int jc = 0; jc < 6; ++jc) { Kg[0][jc] = T(0); Kg[1][jc] = T(0); }
+                if (pin0 && abs_(n1) > T(1e-12)) {
+                  s0 = k0 <= lo0 ? -1 : 1; s1 = 0;
+                  if ((s0 > 0) ? bx.sa_hi : bx.sa_lo) Kg[0][3] = -rcp_(dt);
+                  const T in1 = rcp_(n1);
+                  Kg[1][2] = -m2 * in1; Kg[1][3] = -(m3 + n0 * Kg[0][3]) * in1;
+                } else if (!pin0 && abs_(n0) > T(1e-12)) {
+                  s1 = k1 <= lo_dd ? -1 : 1; s0 = 0;
+                  if (((s1 > 0) ? sd_hi : sd_lo) && b3 > T(1e-12)) { T ib3 = rcp_(b3); Kg[1][2] = -ib3; Kg[1][3] = -a34 * ib3; }
+                  const T in0 = rcp_(n0);
+                  Kg[0][2] = -(m2 + n1 * Kg[1][2]) * in0; Kg[0][3] = -(m3 + n1 * Kg[1][3]) * in0;
+                }
+              }
+            }
+          }
+        }
+      }
+      if (la_carry) {
+        // the line misses this stage's control box (its own controls are saturated too): the same bound, seen through
+        // this stage's dynamics with the controls it did pick, constrains the state of the stage before
+        nx_cth = la_cth; nx_cv = la_cth * a34 + la_cv;
+        nx_r = min_(la_r - (la_cv * dt * k0 + la_cth * b3 * k1), T(0));
+        nx_jump = la_jump;
+        la_next = true;
+      } else
+      // constraint for the stage before this one: steering pinned here.  g = distance of "full steer keeps theta+ inside"
+      // from being tight.  Pinned on the CONSTANT limit (model valid while g >= 0): the state of this stage must keep
+      // g >= 0.  Pinned on the NODE BOUND's edge (model valid while the edge stays inside the constant limit, g <= 0): it
+      // must keep g <= 0.  Either way one half-plane  c'dx >= r  with r <= 0, and the same price for crossing it.
+      if (s1 != 0 && b3 > T(1e-9)) {
+        const T gl = dt * sb_max<T>() * iL;                   // |d theta+ / d v| at the limit
+        const bool on_edge = (s1 > 0) ? sd_hi : sd_lo;
+        const T g = s1 < 0 ? (th - v * gl) + Lim<T>::th_max() : Lim<T>::th_max() - (th + v * gl);
+        const T sg = on_edge ? T(-1) : T(1);                  // keep g >= 0 (constant limit) or g <= 0 (edge)
+        nx_cth = sg * (s1 < 0 ? T(1) : T(-1)); nx_cv = -sg * gl;
+        nx_r = min_(-sg * g, T(0));
+        nx_jump = abs_(Qu[1]) * rcp_(b3);
+        la_next = true;
+      }
+#if defined(MPC_TRACE3) && !defined(__CUDA_ARCH__)
+      if (la_on || la_next) printf("    la k %d on %d carry %d -> next %d c (%.3g %.3g) r %.3g jump %.3g | k %.4g %.4g s %d %d sd %d %d box d [%.4g %.4g] th %.6f\n", k, (int)la_on, (int)la_carry,
+             (int)la_next, (double)nx_cth, (double)nx_cv, (double)nx_r, (double)nx_jump, (double)k0, (double)k1, s0, s1, (int)sd_lo, (int)sd_hi, (double)lo_dd, (double)hi_dd, (double)th);
+#endif
+      la_on = la_next; la_cth = nx_cth; la_cv = nx_cv; la_r = nx_r; la_jump = nx_jump;
+    }
+#endif
 #if defined(MPC_TRACE2) && !defined(__CUDA_ARCH__)
     printf("  k %d Quu %.4g %.4g %.4g Hdd %.4g Qu %.4g %.4g kff %.4g %.4g side %d %d box d [%.4g %.4g] sd %d %d P22 %.4g P33 %.4g p %.3g %.3g %.3g %.3g\n", k, (double)Quu00, (double)Quu01, (double)Quu11, (double)Hdd,
            (double)Qu[0], (double)Qu[1], (double)k0, (double)k1, s0, s1, (double)lo_dd, (double)hi_dd, (int)sd_lo, (int)sd_hi, (double)P[sym6(2,2)], (double)P[sym6(3,3)], (double)pv[0], (double)pv[1], (double)pv[2], (double)pv[3]);
@@ -908,6 +1016,7 @@ template <typename T> MPC_HD bool accept_step(T J, T Jn, T expected) {
 #ifndef MPC_LS_NA
 #define MPC_LS_NA 2
 #endif
+
 #ifndef MPC_LS_RATIO
 #define MPC_LS_RATIO 0.25
 #endif

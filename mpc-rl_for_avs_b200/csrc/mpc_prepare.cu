@@ -195,21 +195,28 @@ k_prepare(const PrepareParams P) {
 
     if (!aborted && has_veh) {
       // ---- intersections of the ego polyline with this vehicle's straight 31-point track ------
-      double Ox[kPred + 1], Oy[kPred + 1];
-      {
-        float fx = (float)ox, fy = (float)oy;            // exact: the observation is float32
-        Ox[0] = ox; Oy[0] = oy;
-        for (int t = 1; t <= kPred; ++t) { fx = fx + tinx; fy = fy + tiny; Ox[t] = fx; Oy[t] = fy; }
-      }
+      // The 31 track points are float32 running sums (see above).  They are NOT kept in an array: a per-thread array is
+      // local memory, and 496 B x 0.5 M threads of it were 90 % of this kernel's DRAM writes (247 MB per launch,
+      // profiles/r02_k_prepare_ncu_full.json vs 19 MB of outputs).  FP32 adds are free here (the kernel is FP64-bound),
+      // so every use walks the sum again from the observed position.
+      const float ox_f = (float)ox, oy_f = (float)oy;    // exact: the observation is float32
+      float ex_f = ox_f, ey_f = oy_f;
+      for (int t = 1; t <= kPred; ++t) { ex_f = ex_f + tinx; ey_f = ey_f + tiny; }
+      const double O0x = ox, O0y = oy, OEx = ex_f, OEy = ey_f;   // track ends
       bool have = false;
       double qx = 0, qy = 0;
-      const double tlen = fabs(Ox[kPred] - Ox[0]) + fabs(Oy[kPred] - Oy[0]);
+      const double tlen = fabs(OEx - O0x) + fabs(OEy - O0y);
       // nearest-time test of a candidate point (agents/pure_mpc.py:641-649), first minimum wins
       auto time_test = [&](double cx, double cy) -> bool {
         int te = 0, to = 0;
         double bde = 1e300, bdo = 1e300;
         for (int t = 0; t < ne; ++t) { double d = dist2(s_ex[g][t] - cx, s_ey[g][t] - cy); if (d < bde) { bde = d; te = t; } }
-        for (int t = 0; t <= kPred; ++t) { double d = dist2(Ox[t] - cx, Oy[t] - cy); if (d < bdo) { bdo = d; to = t; } }
+        float wx = ox_f, wy = oy_f;
+        for (int t = 0; t <= kPred; ++t) {
+          double d = dist2((double)wx - cx, (double)wy - cy);
+          if (d < bdo) { bdo = d; to = t; }
+          wx = wx + tinx; wy = wy + tiny;
+        }
         int dtm = te - to; dtm = dtm < 0 ? -dtm : dtm;
         return dtm < kTimeThreshold;
       };
@@ -220,8 +227,8 @@ k_prepare(const PrepareParams P) {
       int psg[kMaxPieces], npieces = 0;
       double ptx[kMaxPts], pty[kMaxPts];
       int npts = 0;
-      const bool axx = fabs(Ox[kPred] - Ox[0]) >= fabs(Oy[kPred] - Oy[0]);   // scalar coordinate along the track: dominant axis
-      const double o_a = axx ? Ox[0] : Oy[0], o_b = axx ? Ox[kPred] : Oy[kPred];
+      const bool axx = fabs(OEx - O0x) >= fabs(OEy - O0y);   // scalar coordinate along the track: dominant axis
+      const double o_a = axx ? O0x : O0y, o_b = axx ? OEx : OEy;
       const double olo = fmin(o_a, o_b), ohi = fmax(o_a, o_b);
       auto add_point = [&](double cx, double cy) {        // every intersection point, for the GeometryCollection test below
         if (npts < kMaxPts) { ptx[npts] = cx; pty[npts] = cy; ++npts; } else my_deg = 1;
@@ -233,23 +240,27 @@ k_prepare(const PrepareParams P) {
       for (int i = 0; i + 1 < ne; ++i) {
         const double p1x = s_ex[g][i], p1y = s_ey[g][i], p2x = s_ex[g][i + 1], p2y = s_ey[g][i + 1];
         // orientation of track ends about the ego segment is affine in t: locate the sign change
-        const double e0 = orient(p1x, p1y, p2x, p2y, Ox[0], Oy[0]);
-        const double e30 = orient(p1x, p1y, p2x, p2y, Ox[kPred], Oy[kPred]);
+        const double e0 = orient(p1x, p1y, p2x, p2y, O0x, O0y);
+        const double e30 = orient(p1x, p1y, p2x, p2y, OEx, OEy);
         const double sc = (fabs(p2x - p1x) + fabs(p2y - p1y) + 1e-300) * (tlen + 1e-300);
         const double tol = 1e-7 * sc;
         if ((e0 > tol && e30 > tol) || (e0 < -tol && e30 < -tol)) continue;
         // ... and the ego segment must straddle the track's line (most segments whose LINE the track crosses are
         // nowhere near the track itself): same conservative band, the exact predicate below decides the rest
-        const double f1 = orient(Ox[0], Oy[0], Ox[kPred], Oy[kPred], p1x, p1y);
-        const double f2 = orient(Ox[0], Oy[0], Ox[kPred], Oy[kPred], p2x, p2y);
+        const double f1 = orient(O0x, O0y, OEx, OEy, p1x, p1y);
+        const double f2 = orient(O0x, O0y, OEx, OEy, p2x, p2y);
         if ((f1 > tol && f2 > tol) || (f1 < -tol && f2 < -tol)) continue;
         if (e0 == 0.0 && e30 == 0.0 && ohi > olo) {
           // candidate for "this ego segment lies on the track's line": the oracle asks for all four orientations of
           // every segment pair to be exactly zero
           bool allzero = true;
+          float ax_ = ox_f, ay_ = oy_f;
           for (int j = 0; j < kPred && allzero; ++j) {
-            allzero = orient(Ox[j], Oy[j], Ox[j + 1], Oy[j + 1], p1x, p1y) == 0.0 && orient(Ox[j], Oy[j], Ox[j + 1], Oy[j + 1], p2x, p2y) == 0.0 &&
-                      orient(p1x, p1y, p2x, p2y, Ox[j], Oy[j]) == 0.0 && orient(p1x, p1y, p2x, p2y, Ox[j + 1], Oy[j + 1]) == 0.0;
+            const float bx_ = ax_ + tinx, by_ = ay_ + tiny;
+            const double u1x = ax_, u1y = ay_, u2x = bx_, u2y = by_;
+            allzero = orient(u1x, u1y, u2x, u2y, p1x, p1y) == 0.0 && orient(u1x, u1y, u2x, u2y, p2x, p2y) == 0.0 &&
+                      orient(p1x, p1y, p2x, p2y, u1x, u1y) == 0.0 && orient(p1x, p1y, p2x, p2y, u2x, u2y) == 0.0;
+            ax_ = bx_; ay_ = by_;
           }
           const double a = axx ? p1x : p1y, b = axx ? p2x : p2y;
           if (allzero && a != b) {
@@ -275,8 +286,12 @@ k_prepare(const PrepareParams P) {
           jhi = jc + 1 > kPred - 1 ? kPred - 1 : jc + 1;
           if (jlo > kPred - 1 || jhi < 0) continue;
         }
+        float wx = ox_f, wy = oy_f;                        // walk to the first point of the window
+        for (int t = 0; t < jlo; ++t) { wx = wx + tinx; wy = wy + tiny; }
         for (int j = jlo; j <= jhi; ++j) {
-          const double q1x = Ox[j], q1y = Oy[j], q2x = Ox[j + 1], q2y = Oy[j + 1];
+          const float nx_ = wx + tinx, ny_ = wy + tiny;
+          const double q1x = wx, q1y = wy, q2x = nx_, q2y = ny_;
+          wx = nx_; wy = ny_;
           const double d1 = orient(q1x, q1y, q2x, q2y, p1x, p1y);
           const double d2 = orient(q1x, q1y, q2x, q2y, p2x, p2y);
           const double d3 = orient(p1x, p1y, p2x, p2y, q1x, q1y);
@@ -316,7 +331,7 @@ k_prepare(const PrepareParams P) {
           const double c = axx ? ptx[k] : pty[k];
           bool inside = false;
           for (int q = 0; q < npieces; ++q) inside = inside || (plo[q] <= c && c <= phi[q]);
-          if (!inside || orient(Ox[0], Oy[0], Ox[kPred], Oy[kPred], ptx[k], pty[k]) != 0.0) mixed = true;
+          if (!inside || orient(O0x, O0y, OEx, OEy, ptx[k], pty[k]) != 0.0) mixed = true;
         }
         for (int q = 0; q < npieces && !mixed && !have; ++q) {
           // merged vertices of both polylines inside the overlap, ordered along the ego polyline (stable: ego vertices
@@ -333,8 +348,9 @@ k_prepare(const PrepareParams P) {
             key[pos] = kk; vx[pos] = px; vy[pos] = py; ++n;
           };
           for (int t = 0; t < ne; ++t)
-            if (orient(Ox[0], Oy[0], Ox[kPred], Oy[kPred], s_ex[g][t], s_ey[g][t]) == 0.0) insert(s_ex[g][t], s_ey[g][t]);
-          for (int t = 0; t <= kPred; ++t) insert(Ox[t], Oy[t]);
+            if (orient(O0x, O0y, OEx, OEy, s_ex[g][t], s_ey[g][t]) == 0.0) insert(s_ex[g][t], s_ey[g][t]);
+          float wx = ox_f, wy = oy_f;
+          for (int t = 0; t <= kPred; ++t) { insert((double)wx, (double)wy); wx = wx + tinx; wy = wy + tiny; }
           int m = 0;                                      // drop repeated positions (keep the first)
           for (int k = 0; k < n; ++k)
             if (k == 0 || key[k] != key[m - 1]) { key[m] = key[k]; vx[m] = vx[k]; vy[m] = vy[k]; ++m; }

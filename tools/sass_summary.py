@@ -21,7 +21,7 @@ for line in sass.splitlines():
         cur = m.group(1)
         kern[cur] = collections.Counter()
         continue
-    m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
+    m = re.match(r"\s+/\*[0-9a-f]{4,5}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
     if m and cur:
         kern[cur][m.group(1).split(".")[0]] += 1
 usage = {}
