@@ -510,6 +510,70 @@ MPC_HD void box_qp2(T h00, T h01, T h11, T g0, T g1, T lo0, T hi0, T lo1, T hi1,
 // symmetric 6x6 in 21 registers, upper triangle, row-major
 MPC_HD constexpr int sym6(int i, int j) { return i <= j ? (i * (13 - i)) / 2 + (j - i) : (j * (13 - j)) / 2 + (i - j); }
 
+// ---- look-ahead half-plane (see backward_pass) ---------------------------------------------------------------------
+// Minimiser of the stage model 1/2 du'H du + qu'du on the line n'du = r inside the control box, its multiplier, and the
+// feedback gains that keep the line under a perturbation dz of the stage's state (n'du = r - m'dz, m = A'c).  Rare, so
+// kept out of line: the hot sweep only tests  n'k < r.
+template <typename T> struct LaIO {
+  T n0, n1, r, jump, h00, h01, h11, qu0, qu1, lo0, hi0, lo1, hi1, m2, m3, a34;
+  T e03_lo, e03_hi, e12_lo, e12_hi;     // gains of the box edges that come from a node bound (0 = constant limit)
+  T Rz[2][6];
+  T k0, k1;                             // in: box minimiser; out: constrained minimiser
+  T Kg[2][6];
+  int s0, s1;
+  bool applied;
+};
+template <typename T> MPC_NOINLINE void la_constrain(LaIO<T>& io) {
+  io.applied = false;
+  const T n0 = io.n0, n1 = io.n1, nn = n0 * n0 + n1 * n1;
+  if (!(nn > T(1e-20))) return;
+  const T inn = rcp_(nn);
+  const T p0 = io.r * n0 * inn, p1 = io.r * n1 * inn, t0 = -n1, t1 = n0;
+  const T Ht0 = io.h00 * t0 + io.h01 * t1, Ht1 = io.h01 * t0 + io.h11 * t1;
+  const T tHt = t0 * Ht0 + t1 * Ht1;
+  T tlo = T(-1e30), thi = T(1e30);
+  bool feas = tHt > T(0);
+  if (abs_(t0) > T(1e-12)) { const T it = rcp_(t0), u = (io.lo0 - p0) * it, w = (io.hi0 - p0) * it; tlo = max_(tlo, min_(u, w)); thi = min_(thi, max_(u, w)); }
+  else feas = feas && p0 >= io.lo0 - T(1e-6) && p0 <= io.hi0 + T(1e-6);
+  if (abs_(t1) > T(1e-12)) { const T it = rcp_(t1), u = (io.lo1 - p1) * it, w = (io.hi1 - p1) * it; tlo = max_(tlo, min_(u, w)); thi = min_(thi, max_(u, w)); }
+  else feas = feas && p1 >= io.lo1 - T(1e-6) && p1 <= io.hi1 + T(1e-6);
+  if (!feas || tlo > thi) return;                        // the line misses the box (this stage is saturated too)
+  const T tau = -((Ht0 * p0 + Ht1 * p1) + io.qu0 * t0 + io.qu1 * t1) * rcp_(tHt);
+  const T tc = clamp_(tau, tlo, thi);
+  const T c0 = p0 + tc * t0, c1 = p1 + tc * t1;
+  const T lam = (n0 * (io.h00 * c0 + io.h01 * c1 + io.qu0) + n1 * (io.h01 * c0 + io.h11 * c1 + io.qu1)) * inn;
+  if (lam > io.jump) return;                             // crossing the line is worth its price: no constraint this sweep
+  io.applied = true;
+  io.k0 = clamp_(c0, io.lo0, io.hi0); io.k1 = clamp_(c1, io.lo1, io.hi1);
+  for (int jc = 0; jc < 6; ++jc) { io.Kg[0][jc] = T(0); io.Kg[1][jc] = T(0); }
+  if (tc == tau) {                                       // free along the line
+    const T tHn = (Ht0 * n0 + Ht1 * n1) * inn, itHt = rcp_(tHt);
+    for (int jc = 0; jc < 6; ++jc) {
+      const T mj = jc == 2 ? io.m2 : (jc == 3 ? io.m3 : T(0));
+      const T along = (tHn * mj - (t0 * io.Rz[0][jc] + t1 * io.Rz[1][jc])) * itHt;
+      io.Kg[0][jc] = -n0 * inn * mj + t0 * along;
+      io.Kg[1][jc] = -n1 * inn * mj + t1 * along;
+    }
+    io.s0 = 0; io.s1 = 0;
+  } else {                                               // corner of the line and the box: nothing left to choose
+    const bool pin0 = (io.k0 <= io.lo0 || io.k0 >= io.hi0);
+    if (pin0 && abs_(n1) > T(1e-12)) {
+      io.s0 = io.k0 <= io.lo0 ? -1 : 1; io.s1 = 0;
+      io.Kg[0][3] = io.s0 > 0 ? io.e03_hi : io.e03_lo;
+      const T in1 = rcp_(n1);
+      io.Kg[1][2] = -io.m2 * in1; io.Kg[1][3] = -(io.m3 + n0 * io.Kg[0][3]) * in1;
+    } else if (!pin0 && abs_(n0) > T(1e-12)) {
+      io.s1 = io.k1 <= io.lo1 ? -1 : 1; io.s0 = 0;
+      const T e = io.s1 > 0 ? io.e12_hi : io.e12_lo;
+      io.Kg[1][2] = e; io.Kg[1][3] = io.a34 * e;
+      const T in0 = rcp_(n0);
+      io.Kg[0][2] = -(io.m2 + n1 * io.Kg[1][2]) * in0; io.Kg[0][3] = -(io.m3 + n1 * io.Kg[1][3]) * in0;
+    } else {
+      io.s0 = 0; io.s1 = 0;
+    }
+  }
+}
+
 // ---- backward pass -------------------------------------------------------------------------
 // Fills K (2x6 per stage) and F (feed-forward) from the nominal (X, U); returns the two
 // coefficients of the predicted objective change  dJ(alpha) = alpha*d1 + alpha^2*d2.
@@ -538,8 +602,8 @@ MPC_HD void backward_pass(const SolverConfig& cfg, const ProblemScalars<T>& p, c
   // onto the kink instead of moving ALONG it (status "settled on a kink").  la_jump = the first-order price of lifting
   // delta_{k+1} per radian of violation: if the multiplier of the half-plane exceeds it, crossing the line is worth it
   // and the constraint is dropped for this sweep.
-  bool la_on = false;
-  T la_cth = T(0), la_cv = T(0), la_r = T(0), la_jump = T(0);
+  int la_mode = 0;
+  T la_r = T(0), la_jump = T(0);
 #endif
   for (int k = N - 1; k >= 0; --k) {
     const T x = sl.X(k, 0), y = sl.X(k, 1), th = sl.X(k, 2), v = sl.X(k, 3);
@@ -759,94 +823,47 @@ MPC_PRAGMA_UNROLL_OBS
     }
 #if MPC_LOOKAHEAD
     {
-      bool la_next = false;
-      T nx_cth = T(0), nx_cv = T(0), nx_r = T(0), nx_jump = T(0);
-      const T lo0 = bx.lo_a - a, hi0 = bx.hi_a - a;
-      bool la_carry = false;                                  // this stage could not absorb the bound: hand it further back
-      if (la_on) {
-        const T n0 = la_cv * dt, n1 = la_cth * b3;            // B' c
-        const T nn = n0 * n0 + n1 * n1;
-        if (nn > T(1e-20) && n0 * k0 + n1 * k1 < la_r) {
-          la_carry = true;
-          // minimiser of the stage model on the line n'du = la_r inside the control box
-          const T inn = rcp_(nn);
-          const T p0 = la_r * n0 * inn, p1 = la_r * n1 * inn, t0_ = -n1, t1_ = n0;
-          const T Ht0 = h00 * t0_ + h01 * t1_, Ht1 = h01 * t0_ + h11 * t1_;
-          const T tHt = t0_ * Ht0 + t1_ * Ht1;
-          T tlo = T(-1e30), thi = T(1e30);
-          bool feas = tHt > T(0);
-          if (abs_(t0_) > T(1e-12)) { T u = (lo0 - p0) / t0_, w = (hi0 - p0) / t0_; tlo = max_(tlo, min_(u, w)); thi = min_(thi, max_(u, w)); }
-          else feas = feas && p0 >= lo0 - T(1e-6) && p0 <= hi0 + T(1e-6);
-          if (abs_(t1_) > T(1e-12)) { T u = (lo_dd - p1) / t1_, w = (hi_dd - p1) / t1_; tlo = max_(tlo, min_(u, w)); thi = min_(thi, max_(u, w)); }
-          else feas = feas && p1 >= lo_dd - T(1e-6) && p1 <= hi_dd + T(1e-6);
-          if (feas && tlo <= thi) {
-            const T tau = -((Ht0 * p0 + Ht1 * p1) + Qu[0] * t0_ + Qu[1] * t1_) / tHt;
-            const T tc = clamp_(tau, tlo, thi);
-            const T c0 = p0 + tc * t0_, c1 = p1 + tc * t1_;
-            const T lam = (n0 * (h00 * c0 + h01 * c1 + Qu[0]) + n1 * (h01 * c0 + h11 * c1 + Qu[1])) * inn;
-            la_carry = false;
-            if (lam <= la_jump) {
-              k0 = clamp_(c0, lo0, hi0); k1 = clamp_(c1, lo_dd, hi_dd);
-              // the policy keeps the line under a perturbation of this stage's state: n'du = la_r - m'dz, m = A'c
-              const T m2 = la_cth, m3 = la_cth * a34 + la_cv;
-              E00 = f00; E01 = f01; E11 = f11;
-              if (tc == tau) {                                // free along the line
-                const T tHn = (Ht0 * n0 + Ht1 * n1) * inn, itHt = rcp_(tHt);
+      // la_mode: 0 = none; else the half-plane  c'dx >= la_r  of the stage after this one with
+      // c = (c_theta, c_v) = (+1, -gl) [1], (-1, -gl) [2] (steering on its constant limit, lower / upper node bound) or
+      // (-1, +gl) [3], (+1, +gl) [4] (steering on the node bound's own edge), gl = dt sin beta(pi/3) / L
+      const T gl = dt * sb_max<T>() * iL;
+      if (la_mode != 0) {
+        const T cth = (la_mode == 1 || la_mode == 4) ? T(1) : T(-1);
+        const T cv = (la_mode <= 2) ? -gl : gl;
+        const T n0 = cv * dt, n1 = cth * b3;                  // B' c
+        if (n0 * k0 + n1 * k1 < la_r) {                       // rare: the box minimiser crosses the line -> out-of-line solve
+          LaIO<T> io;
+          io.n0 = n0; io.n1 = n1; io.r = la_r; io.jump = la_jump; io.h00 = h00; io.h01 = h01; io.h11 = h11;
+          io.qu0 = Qu[0]; io.qu1 = Qu[1]; io.lo0 = bx.lo_a - a; io.hi0 = bx.hi_a - a; io.lo1 = lo_dd; io.hi1 = hi_dd;
+          io.m2 = cth; io.m3 = cth * a34 + cv;
+          io.e03_lo = bx.sa_lo ? -rcp_(dt) : T(0); io.e03_hi = bx.sa_hi ? -rcp_(dt) : T(0);
+          const bool edge_ok = b3 > T(1e-12);
+          io.e12_lo = (sd_lo && edge_ok) ? -rcp_(b3) : T(0); io.e12_hi = (sd_hi && edge_ok) ? -rcp_(b3) : T(0);
+          io.a34 = a34;
 #pragma unroll
-                for (int jc = 0; jc < 6; ++jc) {
-                  const T mj = jc == 2 ? m2 : (jc == 3 ? m3 : T(0));
-                  const T along = (tHn * mj - (t0_ * Rz[0][jc] + t1_ * Rz[1][jc])) * itHt;
-                  Kg[0][jc] = -n0 * inn * mj + t0_ * along;
-                  Kg[1][jc] = -n1 * inn * mj + t1_ * along;
-                }
-                s0 = 0; s1 = 0;
-              } else {                                        // corner of the line and the box: nothing left to choose
-                const bool pin0 = (k0 <= lo0 || k0 >= hi0);   // which coordinate sits on the box
+          for (int jc = 0; jc < 6; ++jc) { io.Rz[0][jc] = Rz[0][jc]; io.Rz[1][jc] = Rz[1][jc]; }
+          io.k0 = k0; io.k1 = k1;
+          la_constrain(io);
+          if (io.applied) {
+            k0 = io.k0; k1 = io.k1; s0 = io.s0; s1 = io.s1;
+            E00 = f00; E01 = f01; E11 = f11;
 #pragma unroll
-                for (int jc = 0; jc < 6; ++jc) { Kg[0][jc] = T(0); Kg[1][jc] = T(0); }
-                if (pin0 && abs_(n1) > T(1e-12)) {
-                  s0 = k0 <= lo0 ? -1 : 1; s1 = 0;
-                  if ((s0 > 0) ? bx.sa_hi : bx.sa_lo) Kg[0][3] = -rcp_(dt);
-                  const T in1 = rcp_(n1);
-                  Kg[1][2] = -m2 * in1; Kg[1][3] = -(m3 + n0 * Kg[0][3]) * in1;
-                } else if (!pin0 && abs_(n0) > T(1e-12)) {
-                  s1 = k1 <= lo_dd ? -1 : 1; s0 = 0;
-                  if (((s1 > 0) ? sd_hi : sd_lo) && b3 > T(1e-12)) { T ib3 = rcp_(b3); Kg[1][2] = -ib3; Kg[1][3] = -a34 * ib3; }
-                  const T in0 = rcp_(n0);
-                  Kg[0][2] = -(m2 + n1 * Kg[1][2]) * in0; Kg[0][3] = -(m3 + n1 * Kg[1][3]) * in0;
-                }
-              }
-            }
+            for (int jc = 0; jc < 6; ++jc) { Kg[0][jc] = io.Kg[0][jc]; Kg[1][jc] = io.Kg[1][jc]; }
           }
         }
       }
-      if (la_carry) {
-        // the line misses this stage's control box (its own controls are saturated too): the same bound, seen through
-        // this stage's dynamics with the controls it did pick, constrains the state of the stage before
-        nx_cth = la_cth; nx_cv = la_cth * a34 + la_cv;
-        nx_r = min_(la_r - (la_cv * dt * k0 + la_cth * b3 * k1), T(0));
-        nx_jump = la_jump;
-        la_next = true;
-      } else
       // constraint for the stage before this one: steering pinned here.  g = distance of "full steer keeps theta+ inside"
       // from being tight.  Pinned on the CONSTANT limit (model valid while g >= 0): the state of this stage must keep
       // g >= 0.  Pinned on the NODE BOUND's edge (model valid while the edge stays inside the constant limit, g <= 0): it
       // must keep g <= 0.  Either way one half-plane  c'dx >= r  with r <= 0, and the same price for crossing it.
+      la_mode = 0;
       if (s1 != 0 && b3 > T(1e-9)) {
-        const T gl = dt * sb_max<T>() * iL;                   // |d theta+ / d v| at the limit
         const bool on_edge = (s1 > 0) ? sd_hi : sd_lo;
         const T g = s1 < 0 ? (th - v * gl) + Lim<T>::th_max() : Lim<T>::th_max() - (th + v * gl);
-        const T sg = on_edge ? T(-1) : T(1);                  // keep g >= 0 (constant limit) or g <= 0 (edge)
-        nx_cth = sg * (s1 < 0 ? T(1) : T(-1)); nx_cv = -sg * gl;
-        nx_r = min_(-sg * g, T(0));
-        nx_jump = abs_(Qu[1]) * rcp_(b3);
-        la_next = true;
+        la_mode = (s1 < 0 ? 1 : 2) + (on_edge ? 2 : 0);
+        la_r = min_(on_edge ? g : -g, T(0));
+        la_jump = abs_(Qu[1]) * rcp_(b3);
       }
-#if defined(MPC_TRACE3) && !defined(__CUDA_ARCH__)
-      if (la_on || la_next) printf("    la k %d on %d carry %d -> next %d c (%.3g %.3g) r %.3g jump %.3g | k %.4g %.4g s %d %d sd %d %d box d [%.4g %.4g] th %.6f\n", k, (int)la_on, (int)la_carry,
-             (int)la_next, (double)nx_cth, (double)nx_cv, (double)nx_r, (double)nx_jump, (double)k0, (double)k1, s0, s1, (int)sd_lo, (int)sd_hi, (double)lo_dd, (double)hi_dd, (double)th);
-#endif
-      la_on = la_next; la_cth = nx_cth; la_cv = nx_cv; la_r = nx_r; la_jump = nx_jump;
     }
 #endif
 #if defined(MPC_TRACE2) && !defined(__CUDA_ARCH__)

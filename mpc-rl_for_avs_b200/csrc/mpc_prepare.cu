@@ -201,18 +201,36 @@ k_prepare(const PrepareParams P) {
       // so every use walks the sum again from the observed position.
       const float ox_f = (float)ox, oy_f = (float)oy;    // exact: the observation is float32
       float ex_f = ox_f, ey_f = oy_f;
+#pragma unroll 1
       for (int t = 1; t <= kPred; ++t) { ex_f = ex_f + tinx; ey_f = ey_f + tiny; }
       const double O0x = ox, O0y = oy, OEx = ex_f, OEy = ey_f;   // track ends
       bool have = false;
       double qx = 0, qy = 0;
       const double tlen = fabs(OEx - O0x) + fabs(OEy - O0y);
-      // nearest-time test of a candidate point (agents/pure_mpc.py:641-649), first minimum wins
+      // nearest-time test of a candidate point (agents/pure_mpc.py:641-649), first minimum wins.  ONE call site (the
+      // candidate loop below) and rolled loops: inlined at five sites with both 31-point loops unrolled this lambda made
+      // the kernel 8 k instructions, four times the instruction cache.  The nearest TRACK point is searched in a window
+      // of four indices around the projection of the candidate onto the track (the track is straight and its points are
+      // float32 running sums, i.e. equally spaced to ~1e-5 of the spacing, so the squared distance is convex in the
+      // index); slow tracks (spacing below a millimetre) take the full scan.
+      const double trk2 = (OEx - O0x) * (OEx - O0x) + (OEy - O0y) * (OEy - O0y);
       auto time_test = [&](double cx, double cy) -> bool {
         int te = 0, to = 0;
         double bde = 1e300, bdo = 1e300;
+#pragma unroll 1
         for (int t = 0; t < ne; ++t) { double d = dist2(s_ex[g][t] - cx, s_ey[g][t] - cy); if (d < bde) { bde = d; te = t; } }
+        int t_lo = 0, t_hi = kPred;
+        if (trk2 > 1e-3) {                                 // 30 steps of more than a millimetre
+          const double proj = ((cx - O0x) * (OEx - O0x) + (cy - O0y) * (OEy - O0y)) / trk2 * kPred;
+          const int tc = proj < 0.0 ? 0 : (proj > (double)kPred ? kPred : (int)proj);
+          t_lo = tc - 1 < 0 ? 0 : tc - 1;
+          t_hi = tc + 2 > kPred ? kPred : tc + 2;
+        }
         float wx = ox_f, wy = oy_f;
-        for (int t = 0; t <= kPred; ++t) {
+#pragma unroll 1
+        for (int t = 0; t < t_lo; ++t) { wx = wx + tinx; wy = wy + tiny; }
+#pragma unroll 1
+        for (int t = t_lo; t <= t_hi; ++t) {
           double d = dist2((double)wx - cx, (double)wy - cy);
           if (d < bdo) { bdo = d; to = t; }
           wx = wx + tinx; wy = wy + tiny;
@@ -230,12 +248,8 @@ k_prepare(const PrepareParams P) {
       const bool axx = fabs(OEx - O0x) >= fabs(OEy - O0y);   // scalar coordinate along the track: dominant axis
       const double o_a = axx ? O0x : O0y, o_b = axx ? OEx : OEy;
       const double olo = fmin(o_a, o_b), ohi = fmax(o_a, o_b);
-      auto add_point = [&](double cx, double cy) {        // every intersection point, for the GeometryCollection test below
+      auto add_point = [&](double cx, double cy) {        // every intersection point; tested after the scan
         if (npts < kMaxPts) { ptx[npts] = cx; pty[npts] = cy; ++npts; } else my_deg = 1;
-        if (time_test(cx, cy)) {
-          // candidates are visited in lexicographic (x, y) order: keep the smallest passing one
-          if (!have || cx < qx || (cx == qx && cy < qy)) { have = true; qx = cx; qy = cy; }
-        }
       };
       for (int i = 0; i + 1 < ne; ++i) {
         const double p1x = s_ex[g][i], p1y = s_ey[g][i], p2x = s_ex[g][i + 1], p2y = s_ey[g][i + 1];
@@ -255,6 +269,7 @@ k_prepare(const PrepareParams P) {
           // every segment pair to be exactly zero
           bool allzero = true;
           float ax_ = ox_f, ay_ = oy_f;
+#pragma unroll 1
           for (int j = 0; j < kPred && allzero; ++j) {
             const float bx_ = ax_ + tinx, by_ = ay_ + tiny;
             const double u1x = ax_, u1y = ay_, u2x = bx_, u2y = by_;
@@ -287,7 +302,9 @@ k_prepare(const PrepareParams P) {
           if (jlo > kPred - 1 || jhi < 0) continue;
         }
         float wx = ox_f, wy = oy_f;                        // walk to the first point of the window
+#pragma unroll 1
         for (int t = 0; t < jlo; ++t) { wx = wx + tinx; wy = wy + tiny; }
+#pragma unroll 1
         for (int j = jlo; j <= jhi; ++j) {
           const float nx_ = wx + tinx, ny_ = wy + tiny;
           const double q1x = wx, q1y = wy, q2x = nx_, q2y = ny_;
@@ -322,10 +339,11 @@ k_prepare(const PrepareParams P) {
           add_point(p1x + tt * (p2x - p1x), p1y + tt * (p2y - p1y));
         }
       }
+      // ---- candidates in the reference's visiting order, then ONE nearest-time loop --------------------------------
+      bool ordered = false;                               // overlaps: first passing candidate wins; points: lexicographic minimum
       if (npieces > 0) {
         // isolated points that are not part of an overlap make the result a GeometryCollection, for which the
         // reference's dispatch has no branch: no candidate at all
-        have = false;
         bool mixed = false;
         for (int k = 0; k < npts; ++k) {
           const double c = axx ? ptx[k] : pty[k];
@@ -333,7 +351,10 @@ k_prepare(const PrepareParams P) {
           for (int q = 0; q < npieces; ++q) inside = inside || (plo[q] <= c && c <= phi[q]);
           if (!inside || orient(O0x, O0y, OEx, OEy, ptx[k], pty[k]) != 0.0) mixed = true;
         }
-        for (int q = 0; q < npieces && !mixed && !have; ++q) {
+        npts = 0;
+        ordered = true;
+#pragma unroll 1
+        for (int q = 0; q < npieces && !mixed; ++q) {
           // merged vertices of both polylines inside the overlap, ordered along the ego polyline (stable: ego vertices
           // first), one per position; the reference takes coords[len // 2]
           double key[2 * (kPred + 1)], vx[2 * (kPred + 1)], vy[2 * (kPred + 1)];
@@ -347,20 +368,31 @@ k_prepare(const PrepareParams P) {
             for (int m = n; m > pos; --m) { key[m] = key[m - 1]; vx[m] = vx[m - 1]; vy[m] = vy[m - 1]; }
             key[pos] = kk; vx[pos] = px; vy[pos] = py; ++n;
           };
+#pragma unroll 1
           for (int t = 0; t < ne; ++t)
             if (orient(O0x, O0y, OEx, OEy, s_ex[g][t], s_ey[g][t]) == 0.0) insert(s_ex[g][t], s_ey[g][t]);
           float wx = ox_f, wy = oy_f;
+#pragma unroll 1
           for (int t = 0; t <= kPred; ++t) { insert((double)wx, (double)wy); wx = wx + tinx; wy = wy + tiny; }
           int m = 0;                                      // drop repeated positions (keep the first)
           for (int k = 0; k < n; ++k)
             if (k == 0 || key[k] != key[m - 1]) { key[m] = key[k]; vx[m] = vx[k]; vy[m] = vy[k]; ++m; }
-          if (m > 0 && time_test(vx[m / 2], vy[m / 2])) { have = true; qx = vx[m / 2]; qy = vy[m / 2]; }
+          if (m > 0 && npts < kMaxPts) { ptx[npts] = vx[m / 2]; pty[npts] = vy[m / 2]; ++npts; }
         }
+      }
+#pragma unroll 1
+      for (int k = 0; k < npts; ++k) {
+        if (ordered && have) break;
+        const double cx = ptx[k], cy = pty[k];
+        if (!time_test(cx, cy)) continue;
+        // isolated points are visited in lexicographic (x, y) order: keep the smallest passing one
+        if (!have || (!ordered && (cx < qx || (cx == qx && cy < qy)))) { have = true; qx = cx; qy = cy; }
       }
       if (have) {
         my_flag = 1;
         my_qx = qx; my_qy = qy;
         double bdr = 1e300;
+#pragma unroll 1
         for (int j = 0; j < kNRef; ++j) { double d = dist2(s_ref[j][0] - qx, s_ref[j][1] - qy); if (d < bdr) { bdr = d; my_cidx = j; } }
       }
     }
