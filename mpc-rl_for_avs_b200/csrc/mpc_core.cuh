@@ -83,17 +83,6 @@ MPC_HD void sincos_(float x, float* s, float* c) {
   *c = ((q + 1) & 2) ? -cc : cc;
 }
 MPC_HD void sincos_(double x, double* s, double* c) { *s = sin(x); *c = cos(x); }
-// search-direction quality only (backward sweep): the two hardware approximations (MUFU.SIN / MUFU.COS, abs. error ~1e-6
-// on [-pi, pi]) instead of the 35-instruction exact pair -- sincos_ was 11 % of the kernel's executed instructions
-// (profiles/r02_k_solve_source_breakdown.md).  The rollout and the objective keep the exact pair.
-MPC_HD void sincos_dir_(float x, float* s, float* c) {
-#if defined(__CUDA_ARCH__)
-  *s = __sinf(x); *c = __cosf(x);
-#else
-  sincos_(x, s, c);
-#endif
-}
-MPC_HD void sincos_dir_(double x, double* s, double* c) { *s = sin(x); *c = cos(x); }
 // 1/x and a/b: the device path uses the 2-ulp hardware approximations (MUFU + no slow path);
 // every quantity they touch is either a search direction or carries 1e-5 relative tolerance
 MPC_HD float rcp_(float x) {
@@ -336,9 +325,9 @@ MPC_HD int slots_per_problem(int N, int M, bool pack) { return 2 * N + 4 * (N + 
 // q = cos^2 d + 0.25 sin^2 d, cos b = cos d / sqrt q, sin b = 0.5 sin d / sqrt q,
 // beta' = 0.5 / q, beta'' = 0.75 sin d cos d / q^2.
 template <typename T> struct Steer { T sb, cb, g, h; };
-template <typename T, bool kDir = false> MPC_HD Steer<T> steer_terms(T delta, bool second) {
+template <typename T> MPC_HD Steer<T> steer_terms(T delta, bool second) {
   T sd, cd;
-  if (kDir) sincos_dir_(delta, &sd, &cd); else sincos_(delta, &sd, &cd);
+  sincos_(delta, &sd, &cd);
   T q = T(1) - T(0.75) * sd * sd;
   T r = rsqrt_(q);
   Steer<T> o;
@@ -624,9 +613,9 @@ MPC_HD void backward_pass(const SolverConfig& cfg, const ProblemScalars<T>& p, c
     T ap = T(0), dp = T(0);
     if (k > 0) { ap = sl.U(k - 1, 0); dp = sl.U(k - 1, 1); }
     // ---- dynamics derivatives
-    Steer<T> st = steer_terms<T, true>(d, true);
+    Steer<T> st = steer_terms(d, true);
     T sth, cth;
-    sincos_dir_(th, &sth, &cth);
+    sincos_(th, &sth, &cth);
     const T c = cth * st.cb - sth * st.sb, s = sth * st.cb + cth * st.sb;
     const T a13 = -dt * v * s, a14 = dt * c, a23 = dt * v * c, a24 = dt * s, a34 = dt * st.sb * iL;
     const T b1 = a13 * st.g, b2 = a23 * st.g, b3 = dt * v * iL * st.cb * st.g;
