@@ -703,3 +703,22 @@ def test_collision_flags_exact_on_4096_scenes():
             n_lane_hit += bool(res.agent_collide[0])
     assert n_deg <= 0.005 * B and n_col >= 0.1 * B, (n_deg, n_col)
     assert n_lane >= 0.2 * B and n_lane_hit >= 0.1 * n_lane, (n_lane, n_lane_hit)
+
+
+def test_two_handles_on_two_devices_in_one_process():
+    """The opt-in shared-memory size of the solve kernels is a per-DEVICE function attribute: a process that creates
+    handles on two GPUs must be able to launch on both (round 1 remembered it per process).  Needs two visible GPUs."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    pkg = _pkg()
+    B, M = 2048, 8
+    obs, _, _ = pkg.make_scenarios(B, M, seed=3)
+    outs = []
+    for dev in (0, 1):
+        agent = pkg.BatchedPureMPC(CFG, vehicles_count=M + 1, max_batch=B, device=dev, collision_check=True, weight_distance=10.0)
+        with torch.cuda.device(dev):
+            a = agent.predict_batch(obs.to(f"cuda:{dev}"))
+            torch.cuda.synchronize(dev)
+        outs.append(a.cpu())
+        assert torch.isfinite(outs[-1]).all()
+    assert torch.equal(outs[0], outs[1])
