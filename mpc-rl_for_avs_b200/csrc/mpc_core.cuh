@@ -152,13 +152,18 @@ template <typename T> struct RefTab {
   const double* xy;
 };
 template <typename T> struct RefPoint { T x, y, h, sh, ch; };
+// The heading is constant on the two straights of the path (rows 0..39: -pi/2, rows 59..84: -pi, agents/base_agent.py:127-152),
+// so every row of a straight reads the SAME table entry: lanes whose problems sit on a straight -- most of them -- then
+// hit one shared-memory address (a broadcast) instead of 32 divergent rows (bank-conflict replays).  Same values bit for bit.
+MPC_HD int heading_row(int j) { return j < 39 ? 39 : (j > 59 ? 59 : j); }
 template <typename T> MPC_HD RefPoint<T> ref_point(const RefTab<T>& rt, const ProblemScalars<T>& p, int k) {
   int j = p.ego_index + k;                              // j(k) = min(ego_index + k, 84), pure_mpc.py:129
   j = j < kNRef - 1 ? j : kNRef - 1;
   RefPoint<T> r;
   r.x = T(rt.xy[2 * j] - p.x0);
   r.y = T(rt.xy[2 * j + 1] - p.y0);
-  r.h = rt.hsc[j * kRefStride]; r.sh = rt.hsc[j * kRefStride + 1]; r.ch = rt.hsc[j * kRefStride + 2];
+  const int jh = heading_row(j);
+  r.h = rt.hsc[jh * kRefStride]; r.sh = rt.hsc[jh * kRefStride + 1]; r.ch = rt.hsc[jh * kRefStride + 2];
   return r;
 }
 
@@ -171,7 +176,8 @@ MPC_HD RefPoint<T> ref_point(const RefTab<T>& rt, const ProblemScalars<T>& p, co
     j = j < kNRef - 1 ? j : kNRef - 1;
     RefPoint<T> r;
     r.x = sl.R(k, 0); r.y = sl.R(k, 1);
-    r.h = rt.hsc[j * kRefStride]; r.sh = rt.hsc[j * kRefStride + 1]; r.ch = rt.hsc[j * kRefStride + 2];
+    const int jh = heading_row(j);
+    r.h = rt.hsc[jh * kRefStride]; r.sh = rt.hsc[jh * kRefStride + 1]; r.ch = rt.hsc[jh * kRefStride + 2];
     return r;
   } else {
     return ref_point(rt, p, k);

@@ -616,16 +616,35 @@ def polish_fixed_point(prob: Problem, U: np.ndarray, rounds: int = 4, du_tol: fl
     return U, c, False
 
 
-def best_known_optimum(prob: Problem):
+# the start portfolio of the device solver (mpc_core.cuh: start_controls), restated for the CPU side
+PORTFOLIO_STARTS = ((0.0, 0.0, 0), (-5.0, 0.0, 0), (0.0, -0.9, 3), (0.0, 0.4, 3), (5.0, 0.9, 3), (0.0, -0.4, 3), (0.0, -0.4, 1 << 20), (5.0, -0.4, 3))
+
+
+def start_controls(st: int, N: int) -> np.ndarray:
+    a, d, nk = PORTFOLIO_STARTS[st]
+    U = np.zeros((N, 2))
+    U[:, 0] = a
+    U[: min(nk, N), 1] = d
+    return U
+
+
+def best_known_optimum(prob: Problem, cpu_starts: int = 4):
     """The yardstick of the solve-parity tests: the lowest-cost CONFIRMED local optimum found by
-    (a) the IPOPT-like interior point on the literal multiple-shooting NLP from the reference's cold start and
-    (b) SLSQP on the single-shooting form from zero controls, each polished to a fixed point.
-    Returns a dict with the winner and both candidates."""
+    (a) the IPOPT-like interior point on the literal multiple-shooting NLP from the reference's cold start,
+    (b) SLSQP on the single-shooting form from zero controls (the reference's cold start in that form), and
+    (c) SLSQP from the other `cpu_starts - 1` starts of the device solver's portfolio -- so that a first-control
+        disagreement means the device found a different optimum than EVERY CPU run, not merely a better one than a single
+        cold start --
+    each polished to a fixed point.  Returns a dict with the winner and the candidates."""
     r = solve_ipopt_like(prob)
     Ui, ci, oki = polish_fixed_point(prob, r.U)
     s = orc.solve_nlp(prob)
     Us, cs, oks = polish_fixed_point(prob, s.U)
     cands = [("ipm", Ui, ci, oki), ("slsqp", Us, cs, oks)]
+    for st in range(1, cpu_starts):
+        sk = orc.solve_nlp(prob, U0=start_controls(st, prob.N))
+        Uk, ck, okk = polish_fixed_point(prob, sk.U)
+        cands.append((f"slsqp_start{st}", Uk, ck, okk))
     conf = [c for c in cands if c[3]] or cands
     src, Ub, cb, okb = min(conf, key=lambda c: c[2])
     return dict(U=Ub, cost=cb, success=okb, source=src,
