@@ -7,6 +7,8 @@ SURVEY 8-c), so these vectors hold the ORACLE's solutions, not CasADi/IPOPT's; t
 the reference's own code by make_reference_golden.py / golden_reference.npz.  Files:
   golden_track.npz   256 scenarios, M=0, tracking objective (BASELINE config 2 type)
   golden_coll.npz    256 scenarios, M=8, collision check + regeneration + distance cost 10 (config 3 type)
+  golden_holdout.npz 256 more of the config-3 type from another seed: the device solver's start portfolio was selected on
+                     the first two sets, this one only measures
 Each holds the observations (float32), the parsed problem descriptors, collision outputs and the
 oracle's NLP solution from the reference's cold start.
 """
@@ -86,6 +88,10 @@ def make(name, B, M, seed, w_distance, collision_check):
           "collide frac", float(np.mean(d["is_collide"])), "degenerate", int(deg.sum()))
 
 
+SETS = {"golden_track": (256, 0, 11, 0.0, False), "golden_coll": (256, 8, 12, 10.0, True),
+        # hold-out set: never looked at while the device solver's start portfolio and its thresholds were chosen
+        "golden_holdout": (256, 8, 2024, 10.0, True)}
+
 if __name__ == "__main__":
-    make("golden_track", 256, 0, 11, 0.0, False)
-    make("golden_coll", 256, 8, 12, 10.0, True)
+    for name in (sys.argv[1:] or SETS):
+        make(name, *SETS[name])

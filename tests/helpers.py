@@ -207,24 +207,31 @@ def solve_parity_stats(r, g, probs):
       settled  status == 0 or only the kink flag
       below    J_gpu <= J_oracle (1 + 1e-6) + 1e-6 with J evaluated in FP64 by the oracle, oracle = best confirmed
                optimum of the CPU portfolio
+      near     J_gpu <= 1.01 J_oracle (a different optimum, or a point pinned on a kink / on the d = 1 jump of the
+               distance term, whose objective is within 1 % of the best known)
       same     first control within 1e-3 of that optimum;  same_ipm: of the IPOPT-like oracle's"""
     B = len(probs)
     cost64 = np.array([orc.objective(r["U"][i].astype(np.float64), probs[i]) for i in range(B)])
     st = r["status"]
     conv, settled = st == 0, (st & ~SETTLED_MASK) == 0
     below = cost64 <= g["oracle_cost"] * (1 + 1e-6) + 1e-6
+    near = cost64 <= g["oracle_cost"] + 1e-2 * np.maximum(np.abs(g["oracle_cost"]), 1.0)
     same = np.max(np.abs(r["actions"] - g["oracle_U"][:, 0, :]), axis=1) <= 1e-3
     same_ipm = np.max(np.abs(r["actions"] - g["ipm_U"][:, 0, :]), axis=1) <= 1e-3
     out = {"cost64": cost64, "conv_mask": conv, "below_mask": below, "same_mask": same}
     for tag, m in (("all", np.ones(B, bool)), ("in_path", g["in_path"].astype(bool))):
         out[tag] = dict(n=int(m.sum()), conv=float(conv[m].mean()), settled=float(settled[m].mean()), below=float(below[m].mean()),
-                        same=float(same[m].mean()), same_ipm=float(same_ipm[m].mean()))
+                        near=float(near[m].mean()), same=float(same[m].mean()), same_ipm=float(same_ipm[m].mean()))
     return out
 
 
 # measured on the host build of the device code and on the B200 (tools/solve_parity_report.py); thresholds sit a
-# little below the measured rates.  Keys: (golden set, n_starts).
+# little below the measured rates.  Keys: (golden set, n_starts).  golden_holdout was generated after the start
+# portfolio and every solver threshold had been fixed on the other two sets: its rates are the out-of-sample ones
+# (lower: 9 of its 256 scenes end pinned on the d = 1 m jump of the archive distance term, against 1 in golden_coll).
 PARITY_BARS = {
+    ("golden_holdout", 4): dict(in_path=dict(settled=0.94, conv=0.92, below=0.90, near=0.96, same=0.85), all=dict(settled=0.93, below=0.88, near=0.94, same=0.81)),
+    ("golden_holdout", 1): dict(in_path=dict(settled=0.91, conv=0.90, below=0.83, near=0.90, same=0.82), all=dict(settled=0.91, below=0.76, near=0.84, same=0.79)),
     ("golden_track", 4): dict(in_path=dict(settled=0.95, conv=0.95, below=0.95, same=0.92), all=dict(settled=0.95, below=0.91, same=0.86)),
     ("golden_coll", 4): dict(in_path=dict(settled=0.96, conv=0.95, below=0.95, same=0.91), all=dict(settled=0.93, below=0.90, same=0.85)),
     ("golden_track", 1): dict(in_path=dict(settled=0.95, conv=0.95, below=0.91, same=0.90), all=dict(settled=0.95, below=0.83, same=0.83)),

@@ -161,7 +161,7 @@ def _solve_golden(name, M, wd, n_starts):
     return _SOLVE_CACHE[key]
 
 
-@pytest.mark.parametrize("name,M,wd", [("golden_track", 0, 0.0), ("golden_coll", 8, 10.0)])
+@pytest.mark.parametrize("name,M,wd", [("golden_track", 0, 0.0), ("golden_coll", 8, 10.0), ("golden_holdout", 8, 10.0)])
 @pytest.mark.parametrize("n_starts", [4, 1])
 def test_solve_against_best_known_optimum(name, M, wd, n_starts):
     """The solve against the yardstick of oracle/ipm_oracle.py: the best CONFIRMED local optimum found by the
@@ -187,7 +187,7 @@ def test_solve_against_best_known_optimum(name, M, wd, n_starts):
     assert r["iters"].min() >= n_starts
 
 
-@pytest.mark.parametrize("name,M,wd", [("golden_track", 0, 0.0), ("golden_coll", 8, 10.0)])
+@pytest.mark.parametrize("name,M,wd", [("golden_track", 0, 0.0), ("golden_coll", 8, 10.0), ("golden_holdout", 8, 10.0)])
 def test_every_converged_solution_is_confirmed_by_the_oracle(name, M, wd):
     """Started at the GPU's controls, the oracle's NLP solver must stay there: first control within
     1e-3 and no cost reduction beyond 1e-6 relative.  This is the optimality statement that does not

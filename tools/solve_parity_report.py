@@ -18,7 +18,7 @@ def report(name, r, g, probs, verbose=False):
     s = helpers.solve_parity_stats(r, g, probs)
     for tag in ("all", "in_path"):
         o = s[tag]
-        print(f"{name:13s} {tag:8s} n {o['n']:4d} conv {o['conv']:.3f} settled {o['settled']:.3f} | vs best: below {o['below']:.3f} "
+        print(f"{name:13s} {tag:8s} n {o['n']:4d} conv {o['conv']:.3f} settled {o['settled']:.3f} | vs best: below {o['below']:.3f} within 1% {o['near']:.3f} "
               f"same-u0 {o['same']:.3f} | vs ipm: same-u0 {o['same_ipm']:.3f}")
     it, st = r["iters"], r["status"]
     print(f"{'':13s} iters mean {it.mean():.1f} p50 {np.median(it):.0f} p90 {np.percentile(it, 90):.0f} p99 {np.percentile(it, 99):.0f} max {it.max()} | "
@@ -55,5 +55,5 @@ if __name__ == "__main__":
     a = ap.parse_args()
     for S in a.n_starts:
         print(f"==== n_starts {S}")
-        for nm in ("golden_track", "golden_coll"):
+        for nm in ("golden_track", "golden_coll", "golden_holdout"):
             run(nm, a.double, a.verbose, n_starts=S)
