@@ -1061,9 +1061,12 @@ template <typename T> MPC_HD bool accept_step(T J, T Jn, T expected) {
 #endif
 constexpr int kLineSearchPasses = MPC_LS_PASSES;
 constexpr int kStallWindow = 6;        // iterations between progress checkpoints
+constexpr float kConvDecrease = 2.5e-7f;   // predicted relative decrease of the last Newton step at convergence
 
 // bookkeeping after a line search; sets s.done when converged or failed.
-//   (a) converged (status 0): the un-damped full Newton step is accepted and smaller than tol_step;
+//   (a) converged (status 0): the un-damped full Newton step is accepted, smaller than tol_step, and its predicted
+//   decrease is below kConvDecrease relative (a step of 1e-4 can still be worth 3e-5 of the objective when the ego sits
+//   centimetres from an obstacle and the curvature of 1000/d^2 is ~1e9: such a solve takes one more Newton step);
 //   (b) settled on a kink (kStatusKink): over a window of kStallWindow iterations the objective improved by less than
 //   kink_tol relative (floored at the rounding noise of the scalar type) while the last accepted step was below
 //   10 tol_step.  This is how the method ends on points that sit on a kink of the clamped dynamics (a control on its
@@ -1072,13 +1075,13 @@ constexpr int kStallWindow = 6;        // iterations between progress checkpoint
 //   can usually still be improved a little (median 0.2 % of the cost) by moving ALONG the kink (a coordinated change of
 //   several stages that a stage-wise active set cannot represent), so the flag is kept apart from (a).
 template <typename T>
-MPC_HD void after_line_search(const SolverConfig& cfg, SolveState<T>& s, bool accepted, T alpha, T Jn, T maxdu) {
+MPC_HD void after_line_search(const SolverConfig& cfg, SolveState<T>& s, bool accepted, T alpha, T Jn, T maxdu, T expected) {
   s.iter++;
   if (accepted) {
     s.J = Jn;
     s.md_last = maxdu;
     // a small step only proves stationarity when it is the un-damped Newton step
-    if (alpha == T(1) && s.mu == T(0) && maxdu < T(cfg.tol_step)) s.done = true;
+    if (alpha == T(1) && s.mu == T(0) && maxdu < T(cfg.tol_step) && -expected <= T(kConvDecrease) * (abs_(Jn) + T(1))) s.done = true;
     s.mu = s.mu > T(1e-3) ? s.mu * T(MPC_MU_DEC) : T(0);
   } else {
     s.fails++;
@@ -1145,7 +1148,7 @@ MPC_HD void solve_one(const SolverConfig& cfg, const ProblemScalars<T>& p, const
     printf("it %d J %.9g d1 %.4g d2 %.4g alpha %.4g acc %d Jn %.9g maxdu %.3g mu %.3g hs %g u0 %.6f %.6f\n", s.iter, (double)s.J,
            (double)d1, (double)d2, (double)alpha, (int)acc, (double)Jn, (double)md, (double)s.mu, (double)s.hs, (double)sl.U(0, 0), (double)sl.U(0, 1));
 #endif
-    after_line_search(cfg, s, acc, alpha, Jn, md);
+    after_line_search(cfg, s, acc, alpha, Jn, md, alpha * d1 + alpha * alpha * d2);
   }
   if (!(s.J == s.J)) s.status |= kStatusNaN;
 }

@@ -202,7 +202,7 @@ k_solve(const SolverConfig cfg, const MpcProblemBatch batch, const MpcSolveOut o
         solve_init_finish(s, Jn);
         fresh = false;
       } else {
-        after_line_search(cfg, s, acc, alpha, Jn, md);
+        after_line_search(cfg, s, acc, alpha, Jn, md, alpha * d1 + alpha * alpha * d2);
         if (s.done) {
           finish_item(cfg, out, cand, n_starts, idx, sl, s);
           active = false;
@@ -390,7 +390,7 @@ k_solve_tmem(const SolverConfig cfg, const MpcProblemBatch batch, const MpcSolve
     // ---- bookkeeping of the solver state (before the commit sweep: it only needs the line-search results)
     bool commit_me = false;
     if (!kSpec || spec_k == 1) {
-      if (run) { after_line_search(cfg, s, ok, alpha, Jn, md); commit_me = ok; }
+      if (run) { after_line_search(cfg, s, ok, alpha, Jn, md, alpha * d1 + alpha * alpha * d2); commit_me = ok; }
     } else {
       const unsigned okmask = __ballot_sync(full, ok);
       const int gbase = (threadIdx.x & 31) & ~(spec_k - 1);
@@ -398,12 +398,13 @@ k_solve_tmem(const SolverConfig cfg, const MpcProblemBatch batch, const MpcSolve
       const int w = gm ? (__ffs((int)gm) - 1) : spec_k;     // first speculative lane whose step was accepted
       const int src = gbase + (w < spec_k ? w : 0);
       const float a_w = __shfl_sync(full, alpha, src), J_w = __shfl_sync(full, Jn, src), md_w = __shfl_sync(full, md, src);
+      const float ex_w = __shfl_sync(full, alpha * d1 + alpha * alpha * d2, src);
       if (run) {
         int t = 0;
         bool reached = false;
         for (; t < spec_k && !s.done; ++t) {
-          if (t == w) { after_line_search(cfg, s, true, a_w, J_w, md_w); reached = true; ++t; break; }
-          after_line_search(cfg, s, false, 1.f, 0.f, 0.f);
+          if (t == w) { after_line_search(cfg, s, true, a_w, J_w, md_w, ex_w); reached = true; ++t; break; }
+          after_line_search(cfg, s, false, 1.f, 0.f, 0.f, 0.f);
         }
         s.trials = trials0 + MPC_LS_NA * t;
         commit_me = reached && spec_j == w;

@@ -598,19 +598,29 @@ def polish(prob: Problem, U: np.ndarray) -> Solution:
 # ----------------------------------------------------------------------------------------
 # best known optimum of one problem: portfolio of the two CPU solvers + fixed-point polish
 # ----------------------------------------------------------------------------------------
-def polish_fixed_point(prob: Problem, U: np.ndarray, rounds: int = 4, du_tol: float = 1e-3, gain_tol: float = 1e-6):
+def polish_fixed_point(prob: Problem, U: np.ndarray, rounds: int = 4, du_tol: float = 1e-3, gain_tol: float = 1e-6,
+                       viol_tol: float = 1e-3):
     """Repeats SLSQP (single shooting, started at the candidate) until a run neither moves the first
     control by `du_tol` nor lowers the cost by `gain_tol` relative -- the 'oracle confirms it' criterion of
-    the parity tests, applied to the oracle's own candidates.  Returns (U, cost, confirmed)."""
-    U = np.asarray(U, dtype=np.float64)
+    the parity tests, applied to the oracle's own candidates.  Every SLSQP result is first pulled back into the
+    feasible set (mpc_oracle.repair_feasible): SLSQP satisfies the node bounds only to its tolerance, and a failed run
+    can return a grossly infeasible point that would otherwise look like a fixed point with a low cost; a result
+    that violates a bound by more than `viol_tol` is rejected.  Returns (U, cost, confirmed) with U feasible."""
+    U = orc.repair_feasible(np.asarray(U, dtype=np.float64), prob)
     c = orc.objective(U, prob)
     for _ in range(rounds):
         s = orc.solve_nlp(prob, U0=U)
-        if not np.isfinite(s.cost) or s.cost > c + 1e-9 * (1 + abs(c)):
-            return U, c, False                       # SLSQP wandered off: keep the candidate, unconfirmed
-        du0 = float(np.max(np.abs(s.U[0] - U[0])))
-        gain = (c - s.cost) / (1.0 + abs(c))
-        U, c = s.U, s.cost
+        if orc.bound_violation(s.U, prob) > viol_tol:
+            return U, c, False                       # SLSQP failed into the infeasible region
+        Un = orc.repair_feasible(s.U, prob)
+        cn = orc.objective(Un, prob)
+        if not np.isfinite(cn) or cn > c + 1e-9 * (1 + abs(c)):
+            # no feasible improvement: a fixed point if SLSQP did not move either
+            du0 = float(np.max(np.abs(Un[0] - U[0])))
+            return U, c, bool(np.isfinite(cn) and du0 < du_tol and cn <= c + gain_tol * (1 + abs(c)))
+        du0 = float(np.max(np.abs(Un[0] - U[0])))
+        gain = (c - cn) / (1.0 + abs(c))
+        U, c = Un, cn
         if du0 < du_tol and gain < gain_tol:
             return U, c, True
     return U, c, False

@@ -160,6 +160,43 @@ def rollout(s0: np.ndarray, U: np.ndarray, dt: float = 0.1) -> np.ndarray:
     return X
 
 
+def bound_violation(U: np.ndarray, prob_or_s0, dt: float = 0.1) -> float:
+    """Largest violation of the reference's variable bounds (pure_mpc.py:272-280) by the controls U and the
+    states they roll out to: |a| <= 5, |delta| <= pi/3, 0 <= v_k <= 30, |theta_k| <= pi for k = 1..N."""
+    s0 = getattr(prob_or_s0, "s0", prob_or_s0)
+    U = np.asarray(U, dtype=np.float64)
+    X = rollout(np.asarray(s0, dtype=np.float64), U, getattr(prob_or_s0, "dt", dt))
+    return float(max(0.0, np.abs(U[:, 0]).max() - A_MAX, np.abs(U[:, 1]).max() - DELTA_MAX, V_MIN - X[1:, 3].min(),
+                     X[1:, 3].max() - V_MAX, np.abs(X[1:, 2]).max() - TH_MAX))
+
+
+def repair_feasible(U: np.ndarray, prob_or_s0, dt: float = 0.1) -> np.ndarray:
+    """Nearest-in-each-stage feasible controls: walks the horizon and pulls a_k / delta_k back to the edge whenever
+    the bound of pure_mpc.py:272-280 on the control itself or on the NEXT node (v_{k+1}, theta_{k+1}; both are
+    affine in a_k resp. sin beta(delta_k) under the Euler step of :252-254) would be crossed.  SLSQP returns points
+    that violate its inequality constraints by up to its tolerance (and, when it fails, by much more); a yardstick
+    cost has to be the cost of a point of the feasible set, so every SLSQP result goes through here first."""
+    s0 = np.asarray(getattr(prob_or_s0, "s0", prob_or_s0), dtype=np.float64)
+    dt = getattr(prob_or_s0, "dt", dt)
+    U = np.array(U, dtype=np.float64)
+    s = s0.copy()
+    for k in range(U.shape[0]):
+        th, v = s[2], s[3]
+        a = min(max(U[k, 0], -A_MAX), A_MAX)
+        a = min(max(a, (V_MIN - v) / dt), (V_MAX - v) / dt)
+        d = min(max(U[k, 1], -DELTA_MAX), DELTA_MAX)
+        gain = dt * v / WHEELBASE
+        sb = math.sin(math.atan(REAR_RATIO * math.tan(d)))
+        if gain > 0.0 and not (TH_MIN <= th + gain * sb <= TH_MAX):
+            sb_max = math.sin(math.atan(REAR_RATIO * math.tan(DELTA_MAX)))
+            sb = min(max(((TH_MAX if th + gain * sb > TH_MAX else TH_MIN) - th) / gain, -sb_max), sb_max)
+            # inverse of sin beta = 0.5 sin d / sqrt(1 - 0.75 sin^2 d)
+            d = math.asin(min(max(sb / math.sqrt(0.25 + 0.75 * sb * sb), -1.0), 1.0))
+        U[k] = (a, d)
+        s = step(s, U[k], dt)
+    return U
+
+
 def step_jacobians(s: np.ndarray, u: np.ndarray, dt: float) -> Tuple[np.ndarray, np.ndarray]:
     """Analytic A = d s+/d s (4x4), B = d s+/d u (4x2) of `step`."""
     t = math.tan(u[1])
