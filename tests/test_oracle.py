@@ -225,3 +225,29 @@ def test_ipm_oracle_derivatives_and_known_answers():
         r = ipm.solve_ipopt_like(pr)
         assert r.success and not r.restoration and r.constr_viol <= 1e-6
         assert np.max(np.abs(r.u0 - np.array(u0))) <= 1e-5 and abs(r.cost - f) <= 1e-7 * f
+
+
+def test_repair_feasible_projects_onto_the_reference_bounds():
+    """mpc_oracle.repair_feasible: identity on feasible controls, exact feasibility (pure_mpc.py:272-280) otherwise, and
+    the pulled-back stage sits ON the bound it crossed."""
+    rng = np.random.default_rng(5)
+    g = helpers.load_golden("golden_holdout")
+    probs, _ = helpers.problems_from_obs(g["obs"][:32], g["ref_speed"][:32], g["has_ref_speed"][:32],
+                                         w_distance=float(g["w_distance"]), collision_check=True)
+    for i, p in enumerate(probs):
+        U = g["oracle_U"][i]
+        assert orc.bound_violation(U, p) == 0.0                      # the yardstick itself is feasible
+        assert np.array_equal(orc.repair_feasible(U, p), U)
+        W = np.stack([rng.uniform(-9, 9, p.N), rng.uniform(-1.6, 1.6, p.N)], axis=1)
+        R = orc.repair_feasible(W, p)
+        assert orc.bound_violation(R, p) <= 1e-12
+        X = orc.rollout(p.s0, R, p.dt)
+        moved = np.nonzero(np.abs(R - W).max(axis=1) > 0)[0]
+        for k in moved:                                              # every change is explained by an active bound
+            on_a = abs(abs(R[k, 0]) - 5.0) < 1e-12 or min(abs(X[k + 1, 3]), abs(X[k + 1, 3] - 30.0)) < 1e-9
+            on_d = abs(abs(R[k, 1]) - np.pi / 3) < 1e-12 or abs(abs(X[k + 1, 2]) - np.pi) < 1e-9
+            assert (R[k, 0] == W[k, 0] or on_a) and (R[k, 1] == W[k, 1] or on_d), (i, k)
+    # a braking ramp that would drive the speed negative stops exactly at v = 0
+    s0 = np.array([0.0, 0.0, 0.0, 1.0])
+    R = orc.repair_feasible(np.tile([-5.0, 0.0], (20, 1)), s0)
+    assert np.allclose(orc.rollout(s0, R)[2:, 3], 0.0, atol=1e-15) and np.allclose(R[:2, 0], -5.0) and np.allclose(R[2:, 0], 0.0, atol=1e-12)
