@@ -9,6 +9,7 @@ the reference's own code by make_reference_golden.py / golden_reference.npz.  Fi
   golden_coll.npz    256 scenarios, M=8, collision check + regeneration + distance cost 10 (config 3 type)
   golden_holdout.npz 256 more of the config-3 type from another seed: the device solver's start portfolio was selected on
                      the first two sets, this one only measures
+  golden_holdout_1k.npz  1024 more (seed 777), generated last: the out-of-sample rates quoted in DESIGN.md come from here
 Each holds the observations (float32), the parsed problem descriptors, collision outputs and the
 oracle's NLP solution from the reference's cold start.
 """
@@ -90,7 +91,9 @@ def make(name, B, M, seed, w_distance, collision_check):
 
 SETS = {"golden_track": (256, 0, 11, 0.0, False), "golden_coll": (256, 8, 12, 10.0, True),
         # hold-out set: never looked at while the device solver's start portfolio and its thresholds were chosen
-        "golden_holdout": (256, 8, 2024, 10.0, True)}
+        "golden_holdout": (256, 8, 2024, 10.0, True),
+        # the same, four times larger (rates to +-1 %): generated last, never used for a decision
+        "golden_holdout_1k": (1024, 8, 777, 10.0, True)}
 
 if __name__ == "__main__":
     for name in (sys.argv[1:] or SETS):

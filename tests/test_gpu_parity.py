@@ -161,7 +161,8 @@ def _solve_golden(name, M, wd, n_starts):
     return _SOLVE_CACHE[key]
 
 
-@pytest.mark.parametrize("name,M,wd", [("golden_track", 0, 0.0), ("golden_coll", 8, 10.0), ("golden_holdout", 8, 10.0)])
+@pytest.mark.parametrize("name,M,wd", [("golden_track", 0, 0.0), ("golden_coll", 8, 10.0), ("golden_holdout", 8, 10.0),
+                                       ("golden_holdout_1k", 8, 10.0)])
 @pytest.mark.parametrize("n_starts", [4, 1])
 def test_solve_against_best_known_optimum(name, M, wd, n_starts):
     """The solve against the yardstick of oracle/ipm_oracle.py: the best CONFIRMED local optimum found by the

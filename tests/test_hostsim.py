@@ -45,7 +45,8 @@ def test_rollout_cost_matches_oracle(hostsim, name, M, wd, use_double):
         assert abs(tot[i] - to) <= 1e-5 * max(abs(to), 1.0) + p.w_distance * dist_tol
 
 
-@pytest.mark.parametrize("name,M,wd", [("golden_track", 0, 0.0), ("golden_coll", 8, 10.0), ("golden_holdout", 8, 10.0)])
+@pytest.mark.parametrize("name,M,wd", [("golden_track", 0, 0.0), ("golden_coll", 8, 10.0), ("golden_holdout", 8, 10.0),
+                                       ("golden_holdout_1k", 8, 10.0)])
 @pytest.mark.parametrize("n_starts", [1, 4])
 def test_solver_logic_against_golden(hostsim, name, M, wd, n_starts):
     """Host build of the device code against the best known optimum of the CPU portfolio (IPOPT-like interior point on

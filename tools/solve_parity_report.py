@@ -55,5 +55,5 @@ if __name__ == "__main__":
     a = ap.parse_args()
     for S in a.n_starts:
         print(f"==== n_starts {S}")
-        for nm in ("golden_track", "golden_coll", "golden_holdout"):
+        for nm in ("golden_track", "golden_coll", "golden_holdout", "golden_holdout_1k"):
             run(nm, a.double, a.verbose, n_starts=S)
