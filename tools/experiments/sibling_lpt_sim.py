@@ -21,7 +21,7 @@ else:
     lib = helpers.load_hostsim()
     its = []
     for st in range(4):
-        U0 = np.stack([ipm.start_controls(st, 20)] * B).astype(np.float32)
+        U0 = np.stack([ipm.start_controls(st, 20)] * B).astype(np.float32)   # any four starts do for a scheduling study
         its.append(helpers.hostsim_solve_init(lib, d, helpers.hs_config(N=20, M=8, w_distance=10.0), U0=U0, n_starts=1)["iters"])
     its = np.stack(its)            # [4, B]
     np.save(cache, its)
