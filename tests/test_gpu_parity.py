@@ -7,6 +7,8 @@ Tolerances (BASELINE.json north_star / SURVEY 8-c):
   cost                                 J_gpu <= J_oracle (1 + 1e-6) + 1e-6 where the same optimum is found
   collision flags / conflict rows / ego index / latch   exact
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -303,6 +305,46 @@ def test_drop_in_agent_surface():
     # RL hooks: ref_speed (1,1) and weights_from_RL (1,3) as the SB3 subclasses pass them
     u2 = agent.predict(o, ref_speed=np.array([[3.0]]), weights_from_RL=np.array([[1.0, 1.0, 1.0]]))
     assert u2.shape == (2,)
+
+
+def test_raw_ctypes_binding_of_integration_md():
+    """The binding of INTEGRATION.md section 2, executed as written there: the python block is cut out of the document,
+    given a stand-in for the reference's `Agent` base class / `MPC_Action`, and its predict must return what this repo's
+    own host mirror returns for the same observation."""
+    import re
+    import ctypes
+    pkg = _pkg()
+    text = open(os.path.join(helpers.ROOT, "INTEGRATION.md")).read()
+    block = next(b for b in re.findall(r"```python\n(.*?)```", text, flags=re.S) if "class _MpcConfig" in b)
+    block = block.replace('C.CDLL("libmpcb200.so")', f'C.CDLL({pkg._capi.LIB_PATH!r})')
+    block = block.replace("raise TypeError(...)", 'raise TypeError("obs")').replace("raise ValueError(...)", 'raise ValueError("obs")')
+
+    class Agent:                                   # agents/base_agent.py:14-49, the fields the binding reads
+        def __init__(self, env, cfg):
+            self.horizon, self.dt = cfg["horizon"], 1.0 / env.unwrapped.config["policy_frequency"]
+            self.total_vehicles_count = env.unwrapped.config["observation"]["vehicles_count"]
+
+    ns = {"Agent": Agent, "MPC_Action": pkg.MPC_Action}
+    exec(compile(block, "INTEGRATION.md", "exec"), ns)
+
+    class Env:
+        config = {"simulation_frequency": 30, "policy_frequency": 10, "observation": {"vehicles_count": 9}}
+    env = Env()
+    env.unwrapped = env
+    cfg = {"horizon": 20, "render": False, "weight_speed": 1, "weight_control": 1, "weight_input_diff": 1, "ttc_threshold": 3}
+    raw = ns["PureMPC_Agent"](env, cfg)
+    ours = pkg.PureMPC_Agent(env, cfg)
+    obs, _, _ = pkg.make_scenarios(6, 8, seed=77)
+    for i in range(6):
+        o = obs[i].numpy()
+        a, b = raw.predict(o), ours.predict(o)
+        assert a.shape == (2,) and np.array_equal(a, b), (i, a, b)
+        assert raw.is_collide == ours.is_collide
+    with pytest.raises(TypeError):
+        raw.predict([[0] * 8] * 9)
+    with pytest.raises(ValueError):
+        raw.predict(np.zeros((5, 8), np.float32))
+    assert ctypes.sizeof(ns["_MpcConfig"]) == ctypes.sizeof(pkg._capi.MpcConfig)
 
 
 class _StubIntersectionEnv:
