@@ -145,7 +145,10 @@ def _confirm(item):
     U = np.asarray(U, dtype=np.float64)
     c0 = orc.objective(U, prob)
     Us = orc.repair_feasible(orc.solve_nlp(prob, U0=U).U, prob)
-    return bool(np.max(np.abs(Us[0] - U[0])) < 1e-3 and (c0 - orc.objective(Us, prob)) / (1.0 + abs(c0)) < 1e-6)
+    gain = (c0 - orc.objective(Us, prob)) / (1.0 + abs(c0))
+    gain_ok = gain < 1e-6
+    stays = np.max(np.abs(Us[0] - U[0])) < 1e-3 or gain < 4 * 1.1920929e-7     # a valley below FP32 rounding of J is not a disagreement
+    return bool(stays and gain_ok)
 
 
 class _StubEnv:

@@ -967,28 +967,58 @@ enum : int {
 // ---- start portfolio ------------------------------------------------------------------------------
 // The NLP is multi-modal (steering costs 0.01, the Euler slip model admits zig-zag minima, 1/d^2 obstacle
 // potentials): which local optimum a descent method reaches depends on its path.  Start 0 is the reference's
-// own cold start (zero controls, agents/pure_mpc.py:244); starts 1.. are a constant acceleration with or without a
-// short steering pulse, picked greedily from 25 candidates by how often they reach a lower optimum than the starts
-// before them on a 1024-problem tuning set and checked on a separate hold-out set
-// (tools/experiments/start_selection.py).  MpcConfig.n_starts of them are solved per problem and the lowest
-// objective wins.
+// own cold start (zero controls, agents/pure_mpc.py:244).  The others are of two kinds:
+//   path-following   roll the model forward steering at the path point `look` rows ahead of the stage's own
+//                    (the steering angle that turns the heading onto it within the step, clamped to the node box)
+//                    with the acceleration that reaches the stage's reference speed within the step (kAccRef) or
+//                    full braking (kAccBrake);
+//   pulse            a constant acceleration with a short constant steering pulse.
+// Picked greedily from 33 candidates by how often they reach a lower optimum than the starts before them on a
+// 1024-problem tuning set and checked on a separate hold-out set (tools/experiments/start_selection.py).
+// MpcConfig.n_starts of them are solved per problem and the lowest objective wins.
 constexpr int kMaxStarts = 8;
-MPC_HD void start_controls(int st, float* a, float* d, int* nk) {
+enum : int { kStartPulse = 0, kStartPath = 1 };
+enum : int { kAccRef = 0, kAccBrake = 1 };
+struct StartSpec { int kind; float a, d; int n; };    // pulse: (a, d, stages of the pulse); path: (acc mode in n, look-ahead in d)
+MPC_HD StartSpec start_spec(int st) {
   switch (st) {
-    case 1: *a = -5.f; *d = 0.9f; *nk = 3; break;
-    case 2: *a = 0.f; *d = 0.4f; *nk = 3; break;
-    case 3: *a = -5.f; *d = -0.9f; *nk = 3; break;
-    case 4: *a = 0.f; *d = -0.9f; *nk = 1 << 20; break;
-    case 5: *a = 5.f; *d = 0.f; *nk = 0; break;
-    case 6: *a = 0.f; *d = 0.2f; *nk = 3; break;
-    case 7: *a = 5.f; *d = -0.9f; *nk = 3; break;
-    default: *a = 0.f; *d = 0.f; *nk = 0; break;
+    case 1: return {kStartPath, 0.f, 1.f, kAccRef};
+    case 2: return {kStartPath, 0.f, 1.f, kAccBrake};
+    case 3: return {kStartPulse, 0.f, 0.4f, 3};
+    case 4: return {kStartPath, 0.f, 2.f, kAccRef};
+    case 5: return {kStartPulse, -5.f, -0.4f, 3};
+    case 6: return {kStartPath, 0.f, 3.f, kAccRef};
+    case 7: return {kStartPulse, 0.f, 0.2f, 3};
+    default: return {kStartPulse, 0.f, 0.f, 0};
   }
 }
-template <typename T, typename SL> MPC_HD void apply_start(const SolverConfig& cfg, const SL& sl, int st) {
-  float a, d; int nk;
-  start_controls(st, &a, &d, &nk);
-  for (int k = 0; k < cfg.N; ++k) { sl.U(k, 0) = T(a); sl.U(k, 1) = k < nk ? T(d) : T(0); }
+MPC_HD float atan2_(float y, float x) { return atan2f(y, x); }
+MPC_HD double atan2_(double y, double x) { return atan2(y, x); }
+template <typename T, typename SL>
+MPC_HD void apply_start(const SolverConfig& cfg, const ProblemScalars<T>& p, const RefTab<T>& ref, const SL& sl, int st) {
+  const StartSpec sp = start_spec(st);
+  if (sp.kind == kStartPulse) {
+    for (int k = 0; k < cfg.N; ++k) { sl.U(k, 0) = T(sp.a); sl.U(k, 1) = k < sp.n ? T(sp.d) : T(0); }
+    return;
+  }
+  const T dt = T(cfg.dt);
+  const int look = int(sp.d);
+  T x = sl.X(0, 0), y = sl.X(0, 1), th = sl.X(0, 2), v = sl.X(0, 3);
+  for (int k = 0; k < cfg.N; ++k) {
+    const Box<T> bx = control_box(th, v, dt);
+    T a = sp.n == kAccBrake ? -Lim<T>::a_max() : (ref_speed_at(p, k) - v) * rcp_(dt);
+    a = clamp_(clamp_(a, -Lim<T>::a_max(), Lim<T>::a_max()), bx.lo_a, bx.hi_a);
+    const RefPoint<T> r = ref_point(ref, p, k + look);
+    const T ex = r.x - x, ey = r.y - y;
+    T dth = ((ex * ex + ey * ey > T(1e-6)) ? atan2_(ey, ex) : r.h) - th;
+    if (dth > Lim<T>::th_max()) dth -= T(2) * Lim<T>::th_max();
+    if (dth < -Lim<T>::th_max()) dth += T(2) * Lim<T>::th_max();
+    const T gain = dt * max_(v, T(1e-3)) * T(1.0 / 2.5);
+    const T sb = clamp_(clamp_(dth * rcp_(gain), -sb_max<T>(), sb_max<T>()), bx.sb_lo, bx.sb_hi);
+    const T d = delta_of_sinbeta(sb);
+    sl.U(k, 0) = a; sl.U(k, 1) = d;
+    euler_step(x, y, th, v, a, steer_terms(d, false), dt);
+  }
 }
 
 // ---- per-thread solver state -------------------------------------------------------------------
@@ -1130,7 +1160,7 @@ MPC_HD void solve_one(const SolverConfig& cfg, const ProblemScalars<T>& p, const
                       const SL& sl, SolveState<T>& s, const float* u_init = nullptr, int start = 0) {
   {
     solve_init(cfg, sl, s);
-    if (start > 0) apply_start<T>(cfg, sl, start);
+    if (start > 0) apply_start<T>(cfg, p, ref, sl, start);
     if (u_init && start == 0) for (int k = 0; k < cfg.N; ++k) { sl.U(k, 0) = T(u_init[2 * k]); sl.U(k, 1) = T(u_init[2 * k + 1]); }
     T a1 = T(1), J0, md0;
     forward_pass<T, 1, SL>(cfg, p, ref, sl, &a1, true, true, true, &J0, &md0);

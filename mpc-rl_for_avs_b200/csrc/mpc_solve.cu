@@ -111,7 +111,7 @@ __device__ __forceinline__ void begin_item(const SolverConfig& cfg, const MpcPro
   load_problem(batch, B, pb, cfg, p, sl, ref);
   solve_init(cfg, sl, s);
   if (st > 0) {
-    apply_start<float>(cfg, sl, st);
+    apply_start<float>(cfg, p, ref, sl, st);
   } else if (u_init) {                  // opt-in warm start: the first rollout clamps it into the node boxes
 #pragma unroll 1
     for (int k = 0; k < cfg.N; ++k) {
