@@ -51,7 +51,8 @@ def make(name, B, M, seed, w_distance, collision_check):
                collision_check=np.bool_(collision_check), n_obstacles=np.int64(M))
     out.update({"batch_" + k: v for k, v in d.items()})
     # oracle_* = best confirmed optimum of the CPU portfolio (ipm_oracle.best_known_optimum: interior point on the literal
-    # NLP + SLSQP from the reference's cold start + SLSQP from the device solver's other three default starts); ipm_* = the
+    # NLP + SLSQP from the reference's cold start, from three steering-pulse starts and from two path-following starts:
+    # seven runs per problem, every result pulled back into the feasible set); ipm_* = the
     # IPOPT-like interior point on the literal multiple-shooting NLP alone (basin predictor, polished);
     # in_path = the horizon stays on the 85-point path (ego_index + N <= 84): past it the reference point is
     # frozen at the path end while the reference speed is not, and the NLP is ill-posed
