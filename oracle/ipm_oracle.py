@@ -641,11 +641,13 @@ def start_controls(st: int, N: int) -> np.ndarray:
     return U
 
 
-def path_following_controls(prob: Problem, mode: str = "ref", look: int = 1) -> np.ndarray:
+def path_following_controls(prob: Problem, mode: str = "ref", look: int = 1, slalom: bool = False) -> np.ndarray:
     """What a driver would do, as an initial guess: roll the model of pure_mpc.py:220-228 / 252-254 forward steering at
     the path point `look` rows ahead of the stage's own (pure_mpc.py:129 indexing: min(ego_index + k + look, 84)) with the
     steering angle that turns the heading onto it within the step, and with the acceleration that reaches the stage's
     reference speed within the step (`mode` "ref") or full braking ("brake"), inside the bounds of :272-280.
+    `slalom`: from the first stage whose reference row is the frozen last row of the path (k >= 84 - ego_index) the
+    steering alternates full right / full left every stage -- the shape of the optima past the end of the path.
     The device solver's path-following starts (mpc_core.cuh: apply_start) follow the same recipe in FP32."""
     ref = orc.reference_states(prob.dt)
     sb_max = math.sin(math.atan(orc.REAR_RATIO * math.tan(orc.DELTA_MAX)))
@@ -660,6 +662,9 @@ def path_following_controls(prob: Problem, mode: str = "ref", look: int = 1) -> 
         des = math.atan2(ey, ex) if ex * ex + ey * ey > 1e-6 else ref[j, 3]
         dth = math.atan2(math.sin(des - s[2]), math.cos(des - s[2]))
         sb = min(max(dth / (prob.dt * max(s[3], 1e-3) / orc.WHEELBASE), -sb_max), sb_max)
+        k_end = ref.shape[0] - 1 - prob.ego_index
+        if slalom and k >= k_end:
+            sb = sb_max if (k - k_end) & 1 else -sb_max
         U[k] = (a, math.asin(min(max(sb / math.sqrt(0.25 + 0.75 * sb * sb), -1.0), 1.0)))
         s = orc.step(s, U[k], prob.dt)
     return orc.repair_feasible(U, prob)
@@ -671,9 +676,10 @@ def best_known_optimum(prob: Problem, cpu_starts: int = 4, path_starts: int = 2)
     (b) SLSQP on the single-shooting form from zero controls (the reference's cold start in that form),
     (c) SLSQP from `cpu_starts - 1` perturbed starts (PORTFOLIO_STARTS), and
     (d) SLSQP from `path_starts` path-following starts (reference speed, full braking) -- the kind of start that turned
-        out to reach the lowest optimum most often --
-    so that a first-control disagreement means the device found a different optimum than EVERY one of seven CPU runs, not
-    merely a better one than a single cold start; each candidate is polished to a feasible fixed point.  Returns a dict
+        out to reach the lowest optimum most often -- and, when the horizon runs past the end of the path, from the slalom
+        start,
+    so that a first-control disagreement means the device found a different optimum than EVERY one of seven (eight) CPU runs,
+    not merely a better one than a single cold start; each candidate is polished to a feasible fixed point.  Returns a dict
     with the winner and the candidates."""
     r = solve_ipopt_like(prob)
     Ui, ci, oki = polish_fixed_point(prob, r.U)
@@ -688,6 +694,10 @@ def best_known_optimum(prob: Problem, cpu_starts: int = 4, path_starts: int = 2)
         sk = orc.solve_nlp(prob, U0=path_following_controls(prob, mode))
         Uk, ck, okk = polish_fixed_point(prob, sk.U)
         cands.append((f"slsqp_path_{mode}", Uk, ck, okk))
+    if path_starts and prob.ego_index + prob.N > orc.reference_states(prob.dt).shape[0] - 1:
+        sk = orc.solve_nlp(prob, U0=path_following_controls(prob, "ref", 1, slalom=True))
+        Uk, ck, okk = polish_fixed_point(prob, sk.U)
+        cands.append(("slsqp_slalom", Uk, ck, okk))
     conf = [c for c in cands if c[3]] or cands
     src, Ub, cb, okb = min(conf, key=lambda c: c[2])
     return dict(U=Ub, cost=cb, success=okb, source=src,

@@ -240,14 +240,14 @@ def solve_parity_stats(r, g, probs):
 # portfolio and every solver threshold had been fixed on the other two sets: its rates are the out-of-sample ones
 # (lower: 9 of its 256 scenes end pinned on the d = 1 m jump of the archive distance term, against 1 in golden_coll).
 PARITY_BARS = {
-    ("golden_holdout_1k", 4): dict(in_path=dict(settled=0.96, conv=0.95, below=0.94, near=0.97, same=0.91), all=dict(settled=0.95, below=0.885, near=0.93, same=0.86)),
-    ("golden_holdout_1k", 1): dict(in_path=dict(settled=0.92, conv=0.91, below=0.86, near=0.92, same=0.85), all=dict(settled=0.93, below=0.77, near=0.85, same=0.80)),
-    ("golden_holdout", 4): dict(in_path=dict(settled=0.94, conv=0.92, below=0.92, near=0.96, same=0.87), all=dict(settled=0.92, below=0.90, near=0.95, same=0.82)),
-    ("golden_holdout", 1): dict(in_path=dict(settled=0.91, conv=0.90, below=0.83, near=0.90, same=0.82), all=dict(settled=0.91, below=0.76, near=0.84, same=0.79)),
-    ("golden_track", 4): dict(in_path=dict(settled=0.97, conv=0.97, below=0.96, same=0.95), all=dict(settled=0.96, below=0.89, same=0.90)),
-    ("golden_coll", 4): dict(in_path=dict(settled=0.97, conv=0.97, below=0.97, same=0.94), all=dict(settled=0.95, below=0.90, same=0.89)),
-    ("golden_track", 1): dict(in_path=dict(settled=0.95, conv=0.95, below=0.90, same=0.90), all=dict(settled=0.95, below=0.81, same=0.84)),
-    ("golden_coll", 1): dict(in_path=dict(settled=0.91, conv=0.91, below=0.88, same=0.87), all=dict(settled=0.91, below=0.81, same=0.85)),
+    ("golden_holdout_1k", 4): dict(in_path=dict(settled=0.96, conv=0.95, below=0.94, near=0.97, same=0.91), all=dict(settled=0.94, below=0.86, near=0.93, same=0.87)),
+    ("golden_holdout_1k", 1): dict(in_path=dict(settled=0.92, conv=0.91, below=0.86, near=0.92, same=0.85), all=dict(settled=0.93, below=0.77, near=0.84, same=0.80)),
+    ("golden_holdout", 4): dict(in_path=dict(settled=0.94, conv=0.92, below=0.92, near=0.96, same=0.87), all=dict(settled=0.93, below=0.86, near=0.93, same=0.84)),
+    ("golden_holdout", 1): dict(in_path=dict(settled=0.91, conv=0.90, below=0.83, near=0.90, same=0.82), all=dict(settled=0.91, below=0.76, near=0.83, same=0.79)),
+    ("golden_track", 4): dict(in_path=dict(settled=0.97, conv=0.97, below=0.96, same=0.95), all=dict(settled=0.96, below=0.87, same=0.91)),
+    ("golden_coll", 4): dict(in_path=dict(settled=0.97, conv=0.97, below=0.97, same=0.94), all=dict(settled=0.94, below=0.89, same=0.89)),
+    ("golden_track", 1): dict(in_path=dict(settled=0.95, conv=0.95, below=0.90, same=0.90), all=dict(settled=0.95, below=0.80, same=0.84)),
+    ("golden_coll", 1): dict(in_path=dict(settled=0.91, conv=0.91, below=0.88, same=0.87), all=dict(settled=0.91, below=0.79, same=0.83)),
 }
 
 
