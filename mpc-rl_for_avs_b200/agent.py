@@ -53,7 +53,8 @@ class BatchedPureMPC:
 
     n_starts: the NLP is multi-modal, so every problem is solved from `n_starts` starts (0 = the library default, 4)
     and the lowest objective wins; start 0 is the reference's own cold start (zero controls,
-    agents/pure_mpc.py:244) and `n_starts=1` solves only that one (about 4x the throughput)."""
+    agents/pure_mpc.py:244) and `n_starts=1` solves only that one (about 2.5x the throughput); `n_starts=2` adds the
+    path-following start that finds the best optimum most often."""
 
     def __init__(self, cfg: Dict, vehicles_count: int, max_batch: int, device: Union[int, str, torch.device] = 0,
                  dt: float = 0.1, collision_check: bool = True, literal_no_collision: bool = False,
