@@ -976,20 +976,22 @@ enum : int {
 //   slalom           path-following up to the last row of the path, then full steering alternating right / left every
 //                    stage.  Past the end of the 85-point path (ego_index + N > 84) the reference point freezes while
 //                    the reference speed does not, and the optimum is such a slalom; no descent from a
-//                    smooth start finds it.  Start 3 is a pulse for problems whose horizon stays on the path and the
-//                    slalom for the others.
+//                    smooth start finds it.
+// Start 1 is the path-following start for problems whose horizon stays on the path and the slalom for the others;
+// start 3 is a pulse for the former and the path-following start for the latter: the first two starts already hold the
+// most useful one of each kind of problem, the first four hold the same set for every problem as a fixed table would.
 // Picked greedily from 33 candidates by how often they reach a lower optimum than the starts before them on a
 // 1024-problem tuning set and checked on a separate hold-out set (tools/experiments/start_selection.py).
 // MpcConfig.n_starts of them are solved per problem and the lowest objective wins.
 constexpr int kMaxStarts = 8;
-enum : int { kStartPulse = 0, kStartPath = 1, kStartPulseOrSlalom = 2 };
+enum : int { kStartPulse = 0, kStartPath = 1, kStartPathOrSlalom = 2, kStartPulseOrPath = 3 };
 enum : int { kAccRef = 0, kAccBrake = 1 };
 struct StartSpec { int kind; float a, d; int n; };    // pulse: (a, d, stages of the pulse); path: (acc mode in n, look-ahead in d)
 MPC_HD StartSpec start_spec(int st) {
   switch (st) {
-    case 1: return {kStartPath, 0.f, 1.f, kAccRef};
+    case 1: return {kStartPathOrSlalom, 0.f, 1.f, kAccRef};
     case 2: return {kStartPath, 0.f, 1.f, kAccBrake};
-    case 3: return {kStartPulseOrSlalom, 0.f, 0.4f, 3};
+    case 3: return {kStartPulseOrPath, 0.f, 0.4f, 3};
     case 4: return {kStartPath, 0.f, 2.f, kAccRef};
     case 5: return {kStartPulse, -5.f, -0.4f, 3};
     case 6: return {kStartPath, 0.f, 3.f, kAccRef};
@@ -1003,14 +1005,15 @@ template <typename T, typename SL>
 MPC_HD void apply_start(const SolverConfig& cfg, const ProblemScalars<T>& p, const RefTab<T>& ref, const SL& sl, int st) {
   const StartSpec sp = start_spec(st);
   const int k_end = kNRef - 1 - p.ego_index;            // first stage whose reference row is the frozen last one
-  const bool slalom = sp.kind == kStartPulseOrSlalom && k_end < cfg.N;
-  if (sp.kind == kStartPulse || (sp.kind == kStartPulseOrSlalom && !slalom)) {
+  const bool off_path = k_end < cfg.N;
+  const bool slalom = sp.kind == kStartPathOrSlalom && off_path;
+  if (sp.kind == kStartPulse || (sp.kind == kStartPulseOrPath && !off_path)) {
     for (int k = 0; k < cfg.N; ++k) { sl.U(k, 0) = T(sp.a); sl.U(k, 1) = k < sp.n ? T(sp.d) : T(0); }
     return;
   }
   const T dt = T(cfg.dt);
-  const int look = slalom ? 1 : int(sp.d);
-  const bool brake = !slalom && sp.n == kAccBrake;
+  const int look = sp.kind == kStartPulseOrPath ? 1 : int(sp.d);
+  const bool brake = sp.kind == kStartPath && sp.n == kAccBrake;
   T x = sl.X(0, 0), y = sl.X(0, 1), th = sl.X(0, 2), v = sl.X(0, 3);
   for (int k = 0; k < cfg.N; ++k) {
     const Box<T> bx = control_box(th, v, dt);
